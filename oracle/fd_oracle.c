@@ -1,0 +1,294 @@
+/*
+ * fd_oracle.c — CPU ORACLE (test infrastructure; see fd_oracle.h for the header
+ * statement, scope and parity pinning).  Plain C restatement of FiniteDiff.jl's
+ * cached coloured Jacobian driver.  Every block cites the reference file:line it
+ * follows.  Build: gcc -O2 -fno-fast-math -ffp-contract=off [-fopenmp].
+ */
+#include "fd_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+#define PAR_FOR _Pragma("omp parallel for schedule(static) if(nt > 1) num_threads(nt)")
+
+/* src/epsilons.jl:134-144  default_relstep: sqrt(eps) forward, cbrt(eps) central */
+double fdo_default_relstep(int fdtype) {
+  if (fdtype == FDO_FORWARD) return sqrt(DBL_EPSILON);
+  if (fdtype == FDO_CENTRAL) return cbrt(DBL_EPSILON);
+  return 1.0;
+}
+
+/* src/epsilons.jl:26-29 (forward: max(relstep*abs(x),absstep)*dir)
+ * src/epsilons.jl:50-53 (central: max(relstep*abs(x),absstep), dir ignored) */
+double fdo_compute_epsilon(int fdtype, double x, double relstep, double absstep, double dir) {
+  double a = relstep * fabs(x);
+  double e = (a > absstep) ? a : absstep; /* Julia max(); NaN not expected here */
+  if (fdtype == FDO_FORWARD) return e * dir;
+  return e;
+}
+
+/* `maximum(colorvec)` jacobians.jl:547; colorvec===NULL means the default 1:n */
+int64_t fdo_max_color(const int64_t *colorvec, int64_t n) {
+  if (!colorvec) return n;
+  int64_t mx = (n > 0) ? colorvec[0] : 0;
+  for (int64_t j = 1; j < n; ++j)
+    if (colorvec[j] > mx) mx = colorvec[j];
+  return mx;
+}
+
+/* src/jacobians.jl:473-488 */
+int64_t fdo_findstructralnz_dense(const double *A, int64_t m, int64_t n, int64_t *rows, int64_t *cols) {
+  int64_t idx = 0;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < m; ++i)
+      if (A[j * m + i] != 0.0) {
+        if (rows) rows[idx] = i + 1;
+        if (cols) cols[idx] = j + 1;
+        ++idx;
+      }
+  return idx;
+}
+
+static inline int64_t color_of(const int64_t *colorvec, int64_t j0 /*0-based*/) {
+  return colorvec ? colorvec[j0] : j0 + 1;
+}
+
+/* Julia Bool*Float64: x*true = x, x*false = copysign(0.0, x) (a "strong zero") */
+static inline double mul_bool(double v, int b) { return b ? v : copysign(0.0, v); }
+
+/* J[row,col] = v for the (row,col)-addressed storages */
+static inline void setindex_rc(const fdo_problem *P, double *J, int64_t r /*1-based*/, int64_t c, double v) {
+  if (P->j_kind == FDO_J_DENSE) {
+    J[(c - 1) * P->ldJ + (r - 1)] = v;
+  } else { /* FDO_J_BAND: data[u+r-c+1, c], data is (l+u+1) x n column-major (ext/Banded..:22) */
+    int64_t w = P->l + P->u + 1;
+    J[(c - 1) * w + (P->u + r - c)] = v;
+  }
+}
+
+/* One call of the decompression hook for colour `color_i` with vfx = divided differences. */
+static void colorediteration(const fdo_problem *P, double *J, const double *vfx,
+                             const int64_t *colorvec, int64_t color_i, int nt) {
+  const int64_t n = P->n, m = P->m;
+  switch (P->sp_kind) {
+  case FDO_SP_CSC_SAME: {
+    /* ext/FiniteDiffSparseArraysExt.jl:38-47 — nzval[spidx] = vfx[rowval[spidx]] */
+    PAR_FOR
+    for (int64_t c = 0; c < n; ++c) {
+      if (color_of(colorvec, c) == color_i) {
+        for (int64_t p = P->colptr[c]; p <= P->colptr[c + 1] - 1; ++p) {
+          int64_t r = P->rowval[p - 1];
+          J[p - 1] = vfx[r - 1];
+        }
+      }
+    }
+  } break;
+  case FDO_SP_CSC: {
+    /* ext/FiniteDiffSparseArraysExt.jl:20-28 — J[row,col] = vfx[row] */
+    PAR_FOR
+    for (int64_t c = 0; c < n; ++c) {
+      if (color_of(colorvec, c) == color_i) {
+        for (int64_t p = P->colptr[c]; p <= P->colptr[c + 1] - 1; ++p) {
+          int64_t r = P->rowval[p - 1];
+          setindex_rc(P, J, r, c + 1, vfx[r - 1]);
+        }
+      }
+    }
+  } break;
+  case FDO_SP_COO: {
+    /* src/iteration_utils.jl:25-32 — loop over ALL structural nz, colour test per nz */
+    PAR_FOR
+    for (int64_t i = 0; i < P->nnz; ++i) {
+      int64_t c = P->cols_index[i], r = P->rows_index[i];
+      if (color_of(colorvec, c - 1) == color_i) {
+        if (P->j_kind == FDO_J_SLOTS) J[P->slots[i] - 1] = vfx[r - 1];
+        else setindex_rc(P, J, r, c, vfx[r - 1]);
+      }
+    }
+  } break;
+  case FDO_SP_BANDED: {
+    /* ext/FiniteDiffBandedMatricesExt.jl:13-27 — whole in-band column range */
+    int64_t c_lo = (1 - P->l > 1) ? 1 - P->l : 1;        /* max(1,1-l) */
+    int64_t c_hi = (n + P->u < n) ? n + P->u : n;        /* min(ncols,ncols+u) */
+    PAR_FOR
+    for (int64_t c = c_lo; c <= c_hi; ++c) {
+      if (color_of(colorvec, c - 1) == color_i) {
+        int64_t r_lo = (c - P->u > 1) ? c - P->u : 1;    /* max(1,col-u) */
+        int64_t r_hi = (c + P->l < m) ? c + P->l : m;    /* min(nrows,col+l) */
+        for (int64_t r = r_lo; r <= r_hi; ++r) setindex_rc(P, J, r, c, vfx[r - 1]);
+      }
+    }
+  } break;
+  default: break;
+  }
+}
+
+static double norm2(const double *v, int64_t n, int nt) {
+  /* LinearAlgebra.norm(x2) jacobians.jl:560,601.  Restated as sqrt(sum v^2);
+   * sequential summation when single-threaded (bit-level eps unpinned, see header). */
+  double s = 0.0;
+  if (nt > 1) {
+#pragma omp parallel for reduction(+ : s) schedule(static) num_threads(nt)
+    for (int64_t i = 0; i < n; ++i) s += v[i] * v[i];
+  } else {
+    for (int64_t i = 0; i < n; ++i) s += v[i] * v[i];
+  }
+  return sqrt(s);
+}
+
+int fdo_finite_difference_jacobian(const fdo_problem *P, double *J, fdo_fn f, void *ctx,
+                                   double *x, fdo_cache *cache, fdo_opts *o) {
+  if (!P || !J || !f || !x || !cache || !o) return 1;
+  const int64_t m = P->m, n = P->n;                     /* jacobians.jl:515 */
+  const int64_t *colorvec = o->colorvec;                /* :516 (_color = reshape(colorvec,...)) */
+  const int nt = o->nthreads > 1 ? o->nthreads : 1;
+  const int fdtype = o->fdtype;
+  if (fdtype != FDO_FORWARD && fdtype != FDO_CENTRAL) return 2; /* fdtype_error, epsilons.jl:159-167 */
+  double relstep = o->relstep > 0 ? o->relstep : fdo_default_relstep(fdtype); /* :508 */
+  double absstep = o->absstep > 0 ? o->absstep : relstep;                     /* :509 */
+  double dir = o->dir;
+  double *x1 = cache->x1, *x2 = cache->x2, *fx = cache->fx, *fx1 = cache->fx1; /* :518 */
+  o->fcalls = 0;
+
+  /* copyto!(x1, x)  :519 */
+  memcpy(x1, x, (size_t)n * sizeof(double));
+  const double *vfx = fx; /* :520 */
+
+  /* :522-528 rows_index/cols_index come precomputed in P (findstructralnz /
+   * _findstructralnz); nothing for CSC / banded (their ext sets _use_findstructralnz=false). */
+
+  /* fill_matrix!(J,false) when sparsity !== nothing  :530-532; ext/Sparse..:30 fills nzval */
+  if (P->sp_kind != FDO_SP_NONE) memset(J, 0, (size_t)P->j_len * sizeof(double));
+
+  const int64_t maxcolor = fdo_max_color(colorvec, n); /* maximum(colorvec) :547/:589 */
+
+  if (fdtype == FDO_FORWARD) {
+    /* :540-545 */
+    if (!o->f_in) { f(ctx, fx, x); o->fcalls++; vfx = fx; }
+    else vfx = o->f_in;
+
+    for (int64_t color_i = 1; color_i <= maxcolor; ++color_i) { /* :547 */
+      if (P->sp_kind == FDO_SP_NONE) {
+        /* dense column branch :548-557 */
+        double x1_save = x1[color_i - 1];
+        double eps = o->eps_override ? o->eps_override[color_i - 1]
+                                     : fdo_compute_epsilon(FDO_FORWARD, x1_save, relstep, absstep, dir);
+        if (o->eps_out) o->eps_out[color_i - 1] = eps;
+        x1[color_i - 1] = x1_save + eps;
+        f(ctx, fx1, x1); o->fcalls++;
+        double *Jc = J + (color_i - 1) * P->ldJ;
+        PAR_FOR
+        for (int64_t i = 0; i < m; ++i) Jc[i] = (fx1[i] - vfx[i]) / eps; /* :555 */
+        x1[color_i - 1] = x1_save;                                       /* :557 */
+      } else {
+        /* coloured branch :558-585 */
+        PAR_FOR
+        for (int64_t j = 0; j < n; ++j) x2[j] = mul_bool(x1[j], color_of(colorvec, j) == color_i); /* :559 */
+        double tmp = norm2(x2, n, nt);                                                           /* :560 */
+        double eps = o->eps_override ? o->eps_override[color_i - 1]
+                                     : fdo_compute_epsilon(FDO_FORWARD, sqrt(tmp), relstep, absstep, dir); /* :561 */
+        if (o->eps_out) o->eps_out[color_i - 1] = eps;
+        PAR_FOR
+        for (int64_t j = 0; j < n; ++j) x1[j] = x1[j] + mul_bool(eps, color_of(colorvec, j) == color_i);   /* :562 */
+        f(ctx, fx1, x1); o->fcalls++;                                                                     /* :563 */
+        PAR_FOR
+        for (int64_t i = 0; i < m; ++i) fx1[i] = (fx1[i] - vfx[i]) / eps;                                 /* :565 in place */
+        colorediteration(P, J, fx1, colorvec, color_i, nt);                                               /* :566-572 */
+        if (o->no_drift) {
+          PAR_FOR
+          for (int64_t j = 0; j < n; ++j) if (color_of(colorvec, j) == color_i) x1[j] = x[j];
+        } else {
+          PAR_FOR
+          for (int64_t j = 0; j < n; ++j) x1[j] = x1[j] - mul_bool(eps, color_of(colorvec, j) == color_i); /* :584 */
+        }
+      }
+    }
+  } else { /* FDO_CENTRAL :587-622 */
+    for (int64_t color_i = 1; color_i <= maxcolor; ++color_i) { /* :589 */
+      if (P->sp_kind == FDO_SP_NONE) {
+        /* :590-598 */
+        double x_save = x[color_i - 1];
+        double eps = o->eps_override ? o->eps_override[color_i - 1]
+                                     : fdo_compute_epsilon(FDO_CENTRAL, x_save, relstep, absstep, dir);
+        if (o->eps_out) o->eps_out[color_i - 1] = eps;
+        x1[color_i - 1] = x_save + eps;
+        f(ctx, fx1, x1); o->fcalls++;
+        x1[color_i - 1] = x_save - eps;
+        f(ctx, fx, x1); o->fcalls++;
+        double *Jc = J + (color_i - 1) * P->ldJ;
+        const double two_eps = 2 * eps;
+        PAR_FOR
+        for (int64_t i = 0; i < m; ++i) Jc[i] = (fx1[i] - fx[i]) / two_eps; /* :597 */
+        x1[color_i - 1] = x_save;
+      } else {
+        /* :599-621 */
+        PAR_FOR
+        for (int64_t j = 0; j < n; ++j) x2[j] = mul_bool(x1[j], color_of(colorvec, j) == color_i); /* :600 */
+        double tmp = norm2(x2, n, nt);                                                           /* :601 */
+        double eps = o->eps_override ? o->eps_override[color_i - 1]
+                                     : fdo_compute_epsilon(FDO_CENTRAL, sqrt(tmp), relstep, absstep, dir); /* :602 */
+        if (o->eps_out) o->eps_out[color_i - 1] = eps;
+        PAR_FOR
+        for (int64_t j = 0; j < n; ++j) {
+          int b = color_of(colorvec, j) == color_i;
+          x1[j] = x1[j] + mul_bool(eps, b); /* :603 */
+          x[j] = x[j] - mul_bool(eps, b);   /* :604 caller's x perturbed in place */
+        }
+        f(ctx, fx1, x1); o->fcalls++; /* :605 */
+        f(ctx, fx, x); o->fcalls++;   /* :606 */
+        const double two_eps = 2 * eps;
+        PAR_FOR
+        for (int64_t i = 0; i < m; ++i) fx1[i] = (fx1[i] - fx[i]) / two_eps; /* :607 */
+        colorediteration(P, J, fx1, colorvec, color_i, nt);                 /* :608-614 */
+        if (o->no_drift) {
+          /* exact restore (not what the reference does; used to compare with drift-free runs) */
+          PAR_FOR
+          for (int64_t j = 0; j < n; ++j)
+            if (color_of(colorvec, j) == color_i) { x[j] = x[j] + eps; x1[j] = x1[j] - eps; }
+        } else {
+          PAR_FOR
+          for (int64_t j = 0; j < n; ++j) {
+            int b = color_of(colorvec, j) == color_i;
+            x1[j] = x1[j] - mul_bool(eps, b); /* :619 */
+            x[j] = x[j] + mul_bool(eps, b);   /* :620 */
+          }
+        }
+      }
+    }
+  }
+  return 0; /* nothing  :652 */
+}
+
+int fdo_finite_difference_jacobian_cacheless(const fdo_problem *P, double *J, fdo_fn f, void *ctx,
+                                             double *x, fdo_opts *o) {
+  /* jacobians.jl:446-471 */
+  if (!P || !J || !f || !x || !o) return 1;
+  const int64_t m = P->m, n = P->n;
+  fdo_cache c;
+  c.x1 = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  c.x2 = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+  c.fx = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+  c.fx1 = (double *)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
+  if (!c.x1 || !c.x2 || !c.fx || !c.fx1) { free(c.x1); free(c.x2); free(c.fx); free(c.fx1); return 3; }
+  int64_t pre_calls = 0;
+  fdo_opts oo = *o;
+  double *fin_copy = NULL;
+  if (!o->f_in && o->fdtype == FDO_FORWARD) {
+    /* :456-463: fx = zero(x) | zeros(returntype,size(J,1)); f(fx,x); cache = JacobianCache(x,fx,...) */
+    f(ctx, c.fx, x); pre_calls = 1;
+    memcpy(c.fx1, c.fx, sizeof(double) * (size_t)m); /* JacobianCache(x,fx): _fx1 = copy(fx) :72 */
+    oo.f_in = c.fx;                                   /* :469 passes cache.fx as f_in */
+  } else if (o->f_in) {
+    /* :466 cache = JacobianCache(x, f_in, ...): fx = copy(f_in); then f_in := cache.fx (:469) */
+    fin_copy = c.fx;
+    memcpy(c.fx, o->f_in, sizeof(double) * (size_t)m);
+    memcpy(c.fx1, o->f_in, sizeof(double) * (size_t)m);
+    oo.f_in = (o->fdtype == FDO_FORWARD) ? c.fx : NULL;
+  }
+  (void)fin_copy;
+  int rc = fdo_finite_difference_jacobian(P, J, f, ctx, x, &c, &oo);
+  o->fcalls = oo.fcalls + pre_calls;
+  free(c.x1); free(c.x2); free(c.fx); free(c.fx1);
+  return rc;
+}
