@@ -1,0 +1,21 @@
+"""finitediff.jl_b200 — B200 (sm_100a) drop-in for FiniteDiff.jl's coloured sparse-Jacobian hot path.
+
+Layout (only what the path needs):
+    csrc/      hand-written CUDA kernels + the C ABI (libfdjac_b200.so; include/fdjac_b200.h)
+    api.py     host-side mirror of the reference interface (JacobianCache / finite_difference_jacobian!)
+    distributed.py  one-process-per-GPU colour partition + fused gather plumbing
+    julia/     the `ccall` wrapper a Julia host would load (not executable in this image: no julia)
+    _lib.py    ctypes binding of the C ABI (fails loudly if the .so is missing)
+    build.py   nvcc recipe (sm_100a only)
+
+The directory name contains a dot, so it is imported through /root/repo/_bootstrap.py under the alias
+`finitediff_jl_b200`.
+"""
+from . import _lib  # noqa: F401
+from .api import (BandedMatrix, JacobianCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
+                  default_relstep, finite_difference_jacobian_, finite_difference_jacobian_b, make_plan, pinned_empty,
+                  resize_, zeros_colmajor)
+
+__all__ = ["BandedMatrix", "JacobianCache", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
+           "default_relstep", "finite_difference_jacobian_", "finite_difference_jacobian_b", "make_plan",
+           "pinned_empty", "resize_", "zeros_colmajor"]

@@ -1,0 +1,957 @@
+// fdjac_abi.cu — libfdjac_b200.so: plan management + the C ABI declared in include/fdjac_b200.h.
+// B200 / sm_100a only.  There is NO CPU fallback: without a CUDA device every compute entry point fails with
+// FDB_ERR_NO_DEVICE.  Nothing here includes, links or calls anything under oracle/.
+#include "../../include/fdjac_b200.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cmath>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_eps.cuh"
+#include "kernels_perturb.cuh"
+#include "kernels_plan.cuh"
+#include "kernels_scatter.cuh"
+
+using namespace fdb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static fdb_status fail(fdb_status st, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return st;
+}
+
+#define CU(expr)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return fail(FDB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define TRY(expr)                    \
+  do {                               \
+    fdb_status s__ = (expr);         \
+    if (s__ != FDB_OK) return s__;   \
+  } while (0)
+
+enum { SP_NONE = 0, SP_CSC = 1, SP_COO = 3, SP_BANDED = 4 };
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess) {
+      if (prev == dev) ok = true;
+      else ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ plan
+struct fdb_plan {
+  int device = 0, sm_count = 148;
+  int fdtype = FDB_FORWARD, sp_kind = SP_CSC, jkind = FDB_J_CSC_NZVAL;
+  int no_drift = 0;
+  int rank = 0, world = 1;
+  int64_t m = 0, n = 0, E = 0, j_len = 0, ldJ = 0, l = 0, u = 0;
+  int32_t C = 0;
+  int color_bits = 8;
+  bool has_invalid = false;
+  // compressed index streams (device)
+  void *jcolor = nullptr;     // [n] CT
+  int32_t *row32 = nullptr;   // [E]
+  void *ecolor = nullptr;     // [E] CT
+  int64_t *dest = nullptr;    // [E] or null (identity)
+  int32_t *local_of = nullptr;      // [C] device
+  int32_t *d_local_colors = nullptr;// [n_local] device (global colour ids, ascending)
+  std::vector<int32_t> local_colors, owner;
+  // step sizes
+  double *eps = nullptr, *sumsq = nullptr, *partial = nullptr;
+  int eps_blocks = 0;
+  int64_t eps_chunk = 0;
+  // scratch
+  double *fx_own = nullptr, *Fp = nullptr, *Fm = nullptr, *xp = nullptr, *xm = nullptr;
+  int64_t slabs = 0, ldF = 0, ldx = 0, batch = 1, n_groups = 0;
+  // peers (multi-GPU fused gather)
+  double **d_peers = nullptr;
+  int n_peers = 0;
+  // dense-column plans
+  int64_t col_begin = 0, col_end = 0;
+  double *eps_cols = nullptr;
+  // host-buffer path
+  cudaStream_t hstream = nullptr;
+  double *h_dx = nullptr, *h_dJ = nullptr, *h_dfx = nullptr, *h_dfin = nullptr;
+  // bookkeeping
+  std::vector<void *> allocs;
+  size_t device_bytes = 0;
+  fdb_counters_t cnt{};
+  int64_t alg_bytes = 0;
+  int64_t last_eps_count = 0;
+  // optional device-side timing of the scatter launches
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_pool;
+
+  fdb_status alloc(void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+      *p = nullptr;
+      return fail(FDB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    allocs.push_back(*p);
+    device_bytes += bytes;
+    return FDB_OK;
+  }
+  template <typename T> fdb_status alloc_t(T **p, size_t count) { return alloc((void **)p, count * sizeof(T)); }
+  int grid(int64_t items, int per_block = kThreads, int waves = 8) const {
+    int64_t b = (items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sm_count * waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+  }
+};
+
+// A caller-supplied Int64 array that may live on the host or the device: make it readable by kernels.
+struct I64View {
+  const int64_t *d = nullptr;
+  int64_t *owned = nullptr;
+  ~I64View() { if (owned) cudaFree(owned); }
+};
+
+static fdb_status view_i64(const int64_t *p, int64_t count, I64View &v) {
+  if (!p || count <= 0) { v.d = nullptr; return FDB_OK; }
+  cudaPointerAttributes at{};
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { v.d = p; return FDB_OK; }
+  CU(cudaMalloc((void **)&v.owned, (size_t)count * sizeof(int64_t)));
+  CU(cudaMemcpy(v.owned, p, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice));
+  v.d = v.owned;
+  return FDB_OK;
+}
+
+static fdb_status check_device(const fdb_plan_opts *o, int *dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(FDB_ERR_NO_DEVICE, "no CUDA device available (%s): libfdjac_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  int d = 0;
+  if (!o || o->use_current_device || o->device < 0) { CU(cudaGetDevice(&d)); }
+  else d = o->device;
+  if (d >= count) return fail(FDB_ERR_INVALID, "device %d out of range (%d devices)", d, count);
+  *dev = d;
+  return FDB_OK;
+}
+
+template <typename F> static fdb_status dispatch_ct(int bits, F &&fn) {
+  if (bits == 8) return fn((uint8_t)0);
+  if (bits == 16) return fn((uint16_t)0);
+  return fn((int32_t)0);
+}
+
+static const char *plan_err_text(uint32_t e) {
+  if (e & kErrColptr) return "colptr is not a valid CSC column pointer (must start at 1, be non-decreasing, end at nnz+1)";
+  if (e & kErrRowRange) return "row index outside 1..m";
+  if (e & kErrColRange) return "column index outside 1..n";
+  if (e & kErrSlotRange) return "slot outside 1..j_len";
+  if (e & kErrMissingInJ) return "a sparsity entry is absent from J's CSC pattern (the reference would insert a new stored entry; unsupported)";
+  return "invalid pattern";
+}
+
+// colours: max/min, narrow type, per-column colour array
+static fdb_status setup_colors(fdb_plan *P, const int64_t *colorvec /*host or device or null*/, I64View &cv) {
+  const int64_t n = P->n;
+  TRY(view_i64(colorvec, n, cv));
+  long long mx = n, mn = n > 0 ? 1 : 0;
+  if (cv.d && n > 0) {
+    long long *d_mm = nullptr;
+    CU(cudaMalloc((void **)&d_mm, 2 * sizeof(long long)));
+    long long init[2] = {LLONG_MIN, LLONG_MAX};
+    CU(cudaMemcpy(d_mm, init, sizeof init, cudaMemcpyHostToDevice));
+    color_minmax<<<P->grid(n), kThreads>>>(cv.d, n, d_mm, d_mm + 1);
+    long long out[2];
+    cudaError_t e = cudaMemcpy(out, d_mm, sizeof out, cudaMemcpyDeviceToHost);
+    cudaFree(d_mm);
+    if (e != cudaSuccess) return fail(FDB_ERR_CUDA, "colour min/max failed: %s", cudaGetErrorString(e));
+    mx = out[0];
+    mn = out[1];
+  }
+  if (n == 0) mx = 0;
+  if (mx < 0) mx = 0;                       // maximum(colorvec) < 1: the colour loop 1:max is empty
+  if (mx > 0x7FFFFFF0LL) return fail(FDB_ERR_UNSUPPORTED, "maximum(colorvec) = %lld exceeds 2^31", mx);
+  P->C = (int32_t)mx;
+  P->has_invalid = n > 0 && mn < 1;
+  P->color_bits = mx <= 255 ? 8 : (mx <= 65535 ? 16 : 32);
+  TRY(P->alloc(&P->jcolor, (size_t)std::max<int64_t>(n, 1) * (P->color_bits / 8)));
+  if (n > 0) {
+    TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      convert_colors<CT><<<P->grid(n), kThreads>>>(cv.d, n, (CT *)P->jcolor);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+  }
+  return FDB_OK;
+}
+
+// colour ownership (multi-GPU), local colour list, scratch sizing
+static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const std::vector<unsigned long long> &count) {
+  const int32_t C = P->C;
+  P->owner.assign(C, 0);
+  const int world = P->world;
+  if (world > 1) {
+    if (o && o->partition == 1) {
+      // LPT: heaviest colour first onto the least-loaded rank (ties -> lowest rank), deterministic on every rank
+      std::vector<int32_t> order(C);
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return count[a] > count[b]; });
+      std::vector<unsigned long long> load(world, 0);
+      for (int32_t k : order) {
+        int best = 0;
+        for (int r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
+        P->owner[k] = best;
+        load[best] += count[k] + 1;
+      }
+    } else {
+      for (int32_t k = 0; k < C; ++k) P->owner[k] = k % world;
+    }
+  }
+  std::vector<int32_t> local_of(C, -1);
+  P->local_colors.clear();
+  for (int32_t k = 0; k < C; ++k)
+    if (P->owner[k] == P->rank) { local_of[k] = (int32_t)P->local_colors.size(); P->local_colors.push_back(k); }
+  const int64_t n_local = (int64_t)P->local_colors.size();
+  TRY(P->alloc_t(&P->local_of, std::max<int32_t>(C, 1)));
+  TRY(P->alloc_t(&P->d_local_colors, std::max<int64_t>(n_local, 1)));
+  if (C > 0) CU(cudaMemcpy(P->local_of, local_of.data(), (size_t)C * 4, cudaMemcpyHostToDevice));
+  if (n_local > 0) CU(cudaMemcpy(P->d_local_colors, P->local_colors.data(), (size_t)n_local * 4, cudaMemcpyHostToDevice));
+
+  // step-size buffers
+  TRY(P->alloc_t(&P->eps, std::max<int32_t>(C, 1)));
+  TRY(P->alloc_t(&P->sumsq, std::max<int32_t>(C, 1)));
+  {
+    int64_t nb = (P->n + 2047) / 2048;
+    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * 8));
+    P->eps_blocks = (int)nb;
+    int64_t chunk = (P->n + nb - 1) / nb;
+    P->eps_chunk = std::max<int64_t>(chunk, 1);
+    const int64_t stride = C <= kEpsRegColors ? kEpsRegColors : std::min<int64_t>(C, kEpsWindow);
+    TRY(P->alloc_t(&P->partial, (size_t)nb * stride));
+  }
+
+  // scratch: stacked f! outputs (slabs) + perturbed points
+  const bool central = P->fdtype == FDB_CENTRAL;
+  P->ldF = (P->m + 1) & ~(int64_t)1;
+  P->ldx = (P->n + 1) & ~(int64_t)1;
+  if (P->ldF < 2) P->ldF = 2;
+  if (P->ldx < 2) P->ldx = 2;
+  int64_t budget = (o && o->scratch_bytes > 0) ? o->scratch_bytes : (int64_t)8 << 30;
+  const int64_t per_slab = 8 * P->ldF * (central ? 2 : 1);
+  int64_t slabs = std::max<int64_t>(1, budget / per_slab);
+  slabs = std::min<int64_t>(slabs, std::max<int64_t>(n_local, 1));
+  P->slabs = slabs;
+  P->n_groups = n_local == 0 ? 0 : (n_local + slabs - 1) / slabs;
+  int64_t batch = (o && o->max_batch > 1) ? o->max_batch : 1;
+  batch = std::min<int64_t>(batch, slabs);
+  P->batch = batch;
+  TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
+  TRY(P->alloc_t(&P->Fp, (size_t)slabs * P->ldF));
+  TRY(P->alloc_t(&P->xp, (size_t)batch * P->ldx));
+  if (central) {
+    TRY(P->alloc_t(&P->Fm, (size_t)slabs * P->ldF));
+    TRY(P->alloc_t(&P->xm, (size_t)batch * P->ldx));
+  }
+  return FDB_OK;
+}
+
+static fdb_status read_plan_err(uint32_t *d_err, const char *what) {
+  uint32_t h = 0;
+  CU(cudaMemcpy(&h, d_err, 4, cudaMemcpyDeviceToHost));
+  const uint32_t hard = h & ~(uint32_t)(kErrPatternDiff | kErrRowOrder);
+  if (hard == kErrMissingInJ) return fail(FDB_ERR_UNSUPPORTED, "%s: %s", what, plan_err_text(hard));
+  if (hard) return fail(FDB_ERR_INVALID, "%s: %s", what, plan_err_text(hard));
+  return FDB_OK;
+}
+
+static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, int64_t n) {
+  if (!out) return fail(FDB_ERR_INVALID, "plan output pointer is NULL");
+  *out = nullptr;
+  if (m < 0 || n < 0) return fail(FDB_ERR_INVALID, "negative dimensions m=%lld n=%lld", (long long)m, (long long)n);
+  if (m > 0x7FFFFFF0LL || n > 0x7FFFFFF0LL) return fail(FDB_ERR_UNSUPPORTED, "m, n must be < 2^31");
+  if (o && o->fdtype != FDB_FORWARD && o->fdtype != FDB_CENTRAL)
+    return fail(FDB_ERR_UNSUPPORTED, "Unrecognized fdtype: valid values are forward (0) and central (1)");
+  int dev = 0;
+  TRY(check_device(o, &dev));
+  fdb_plan *P = new (std::nothrow) fdb_plan();
+  if (!P) return fail(FDB_ERR_NOMEM, "out of host memory");
+  P->device = dev;
+  P->m = m;
+  P->n = n;
+  P->fdtype = o ? o->fdtype : FDB_FORWARD;
+  P->no_drift = o ? o->no_drift : 0;
+  P->world = (o && o->world > 1) ? o->world : 1;
+  P->rank = (o && o->world > 1) ? o->rank : 0;
+  if (P->rank < 0 || P->rank >= P->world) { delete P; return fail(FDB_ERR_INVALID, "rank %d outside world %d", P->rank, P->world); }
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { delete P; return fail(FDB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+  P->sm_count = prop.multiProcessorCount;
+  *out = P;
+  return FDB_OK;
+}
+
+static void free_plan(fdb_plan *P) {
+  if (!P) return;
+  DeviceGuard g(P->device);
+  for (void *p : P->allocs) cudaFree(p);
+  for (auto &ev : P->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto &ev : P->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (P->hstream) cudaStreamDestroy(P->hstream);
+  delete P;
+}
+
+#define PLAN_TRY(expr)                                   \
+  do {                                                   \
+    fdb_status s__ = (expr);                             \
+    if (s__ != FDB_OK) { free_plan(P); *plan = nullptr; return s__; } \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ exported: misc
+extern "C" {
+
+int fdb_abi_version(void) { return FDB_ABI_VERSION; }
+const char *fdb_last_error(void) { return g_err.c_str(); }
+int fdb_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+// src/epsilons.jl:134-144
+double fdb_default_relstep(int fdtype) {
+  if (fdtype == FDB_FORWARD) return sqrt(DBL_EPSILON);
+  if (fdtype == FDB_CENTRAL) return cbrt(DBL_EPSILON);
+  return 1.0;
+}
+// src/epsilons.jl:26-29 / :50-53
+double fdb_compute_epsilon(int fdtype, double x, double relstep, double absstep, double dir) {
+  const double a = relstep * fabs(x);
+  const double e = a > absstep ? a : absstep;
+  return fdtype == FDB_FORWARD ? e * dir : e;
+}
+
+// ------------------------------------------------------------------------------------------------ plan creation
+fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                               int jkind, const int64_t *j_colptr, const int64_t *j_rowval, int64_t ldJ,
+                               const int64_t *colorvec, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, m, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  if (!colptr) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "colptr is NULL"); }
+  if (jkind != FDB_J_CSC_NZVAL && jkind != FDB_J_DENSE) {
+    free_plan(P); *plan = nullptr;
+    return fail(FDB_ERR_INVALID, "CSC sparsity supports J kinds CSC_NZVAL and DENSE");
+  }
+  P->sp_kind = SP_CSC;
+  P->jkind = jkind;
+  // nnz = colptr[n]-1 : read the last element wherever it lives
+  I64View cp, rv, cv, jcp, jrv;
+  PLAN_TRY(view_i64(colptr, n + 1, cp));
+  int64_t last = 1;
+  {
+    cudaError_t e = cudaMemcpy(&last, cp.d + n, 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "reading colptr[n]: %s", cudaGetErrorString(e)); }
+  }
+  const int64_t nnz = last - 1;
+  if (nnz < 0 || nnz > 0x7FFFFFF0LL) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_UNSUPPORTED, "nnz=%lld unsupported (must be in [0, 2^31))", (long long)nnz); }
+  if (nnz > 0 && !rowval) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "rowval is NULL"); }
+  P->E = nnz;
+  PLAN_TRY(view_i64(rowval, nnz, rv));
+  PLAN_TRY(setup_colors(P, colorvec, cv));
+
+  uint32_t *d_err = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  PLAN_TRY(P->alloc_t(&d_err, 1));
+  PLAN_TRY(P->alloc_t(&d_cnt, std::max<int32_t>(P->C, 1)));
+  cudaMemset(d_err, 0, 4);
+  cudaMemset(d_cnt, 0, (size_t)std::max<int32_t>(P->C, 1) * 8);
+  PLAN_TRY(P->alloc_t(&P->row32, std::max<int64_t>(nnz, 4)));
+  PLAN_TRY(P->alloc(&P->ecolor, (size_t)std::max<int64_t>(nnz, 4) * (P->color_bits / 8) + 16));
+
+  bool same_pattern = true;
+  bool other_csc = false;
+  if (jkind == FDB_J_CSC_NZVAL && j_colptr && j_rowval && (j_colptr != colptr || j_rowval != rowval)) {
+    // ext/FiniteDiffSparseArraysExt.jl:51-52
+    PLAN_TRY(view_i64(j_colptr, n + 1, jcp));
+    int64_t jlast = 1;
+    cudaMemcpy(&jlast, jcp.d + n, 8, cudaMemcpyDeviceToHost);
+    const int64_t jnnz = jlast - 1;
+    PLAN_TRY(view_i64(j_rowval, jnnz, jrv));
+    if (jnnz != nnz) same_pattern = false;
+    else {
+      compare_i64<<<P->grid(n + 1), kThreads>>>(cp.d, jcp.d, n + 1, d_err);
+      if (nnz > 0) compare_i64<<<P->grid(nnz), kThreads>>>(rv.d, jrv.d, nnz, d_err);
+      uint32_t h = 0;
+      cudaMemcpy(&h, d_err, 4, cudaMemcpyDeviceToHost);
+      same_pattern = !(h & kErrPatternDiff);
+      cudaMemset(d_err, 0, 4);
+    }
+    other_csc = !same_pattern;
+    P->j_len = jnnz;
+  } else if (jkind == FDB_J_CSC_NZVAL) {
+    P->j_len = nnz;
+  } else {
+    if (ldJ < m) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "ldJ=%lld < m=%lld", (long long)ldJ, (long long)m); }
+    P->ldJ = ldJ;
+    P->j_len = ldJ * n;
+  }
+  const bool need_dest = jkind == FDB_J_DENSE || other_csc;
+  int32_t *col32 = nullptr;
+  if (need_dest) {
+    PLAN_TRY(P->alloc_t(&col32, std::max<int64_t>(nnz, 1)));
+    PLAN_TRY(P->alloc_t(&P->dest, std::max<int64_t>(nnz, 1)));
+  }
+  validate_colptr<<<P->grid(n + 1), kThreads>>>(cp.d, n, nnz, d_err);
+  PLAN_TRY(read_plan_err(d_err, "CSC sparsity"));
+  if (nnz > 0) {
+    PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      expand_csc<CT><<<P->grid(nnz), kThreads>>>(cp.d, rv.d, m, n, nnz, (const CT *)P->jcolor, P->C, P->row32,
+                                                 (CT *)P->ecolor, col32, d_cnt, d_err);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+    if (jkind == FDB_J_DENSE) dest_dense_from_rc<<<P->grid(nnz), kThreads>>>(P->row32, col32, nnz, ldJ, P->dest);
+    else if (other_csc) dest_other_csc<<<P->grid(nnz), kThreads>>>(P->row32, col32, nnz, jcp.d, jrv.d, P->dest, d_err);
+  }
+  PLAN_TRY(read_plan_err(d_err, "CSC sparsity"));
+  std::vector<unsigned long long> cnt(std::max<int32_t>(P->C, 1), 0);
+  if (P->C > 0) {
+    cudaError_t e = cudaMemcpy(cnt.data(), d_cnt, (size_t)P->C * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "colour counts: %s", cudaGetErrorString(e)); }
+  }
+  PLAN_TRY(finish_colored_plan(P, opts, cnt));
+  // B_alg = 32*nnz + 16*n + 8 (valid colouring; Int64 indices as at the ABI)
+  P->alg_bytes = 32 * nnz + 16 * n + 8;
+  {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "plan build: %s", cudaGetErrorString(e)); }
+  }
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_create_coo(fdb_plan **plan, int64_t m, int64_t n, int64_t nnz, const int64_t *rows_index,
+                               const int64_t *cols_index, int jkind, const int64_t *slots, int64_t ldJ_or_jlen,
+                               const int64_t *colorvec, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, m, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  if (nnz < 0 || nnz > 0x7FFFFFF0LL) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_UNSUPPORTED, "nnz=%lld unsupported", (long long)nnz); }
+  if (nnz > 0 && (!rows_index || !cols_index)) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "rows_index/cols_index NULL"); }
+  if (jkind != FDB_J_DENSE && jkind != FDB_J_SLOTS) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "COO sparsity supports J kinds DENSE and SLOTS"); }
+  if (jkind == FDB_J_SLOTS && nnz > 0 && !slots) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "slots is NULL"); }
+  if (jkind == FDB_J_DENSE && ldJ_or_jlen < m) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "ldJ < m"); }
+  P->sp_kind = SP_COO;
+  P->jkind = jkind;
+  P->E = nnz;
+  if (jkind == FDB_J_DENSE) { P->ldJ = ldJ_or_jlen; P->j_len = ldJ_or_jlen * n; }
+  else P->j_len = ldJ_or_jlen;
+  I64View rv, cvw, sv, cv;
+  PLAN_TRY(view_i64(rows_index, nnz, rv));
+  PLAN_TRY(view_i64(cols_index, nnz, cvw));
+  if (jkind == FDB_J_SLOTS) PLAN_TRY(view_i64(slots, nnz, sv));
+  PLAN_TRY(setup_colors(P, colorvec, cv));
+  uint32_t *d_err = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  PLAN_TRY(P->alloc_t(&d_err, 1));
+  PLAN_TRY(P->alloc_t(&d_cnt, std::max<int32_t>(P->C, 1)));
+  cudaMemset(d_err, 0, 4);
+  cudaMemset(d_cnt, 0, (size_t)std::max<int32_t>(P->C, 1) * 8);
+  PLAN_TRY(P->alloc_t(&P->row32, std::max<int64_t>(nnz, 4)));
+  PLAN_TRY(P->alloc(&P->ecolor, (size_t)std::max<int64_t>(nnz, 4) * (P->color_bits / 8) + 16));
+  PLAN_TRY(P->alloc_t(&P->dest, std::max<int64_t>(nnz, 1)));
+  if (nnz > 0) {
+    PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      prepare_coo<CT><<<P->grid(nnz), kThreads>>>(rv.d, cvw.d, jkind == FDB_J_SLOTS ? sv.d : nullptr, nnz, m, n, P->ldJ,
+                                                  P->j_len, (const CT *)P->jcolor, P->C, P->row32, (CT *)P->ecolor,
+                                                  P->dest, d_cnt, d_err);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+  }
+  PLAN_TRY(read_plan_err(d_err, "COO sparsity"));
+  std::vector<unsigned long long> cnt(std::max<int32_t>(P->C, 1), 0);
+  if (P->C > 0) cudaMemcpy(cnt.data(), d_cnt, (size_t)P->C * 8, cudaMemcpyDeviceToHost);
+  PLAN_TRY(finish_colored_plan(P, opts, cnt));
+  P->alg_bytes = 32 * nnz + 16 * n + 8;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "plan build: %s", cudaGetErrorString(e)); }
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_create_banded(fdb_plan **plan, int64_t m, int64_t n, int64_t l, int64_t u, int jkind, int64_t ldJ,
+                                  const int64_t *colorvec, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, m, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  if (jkind != FDB_J_BAND && jkind != FDB_J_DENSE) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "banded sparsity supports J kinds BAND and DENSE"); }
+  if (l + u + 1 < 1 || l < -n || u < -m) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "invalid bandwidths l=%lld u=%lld", (long long)l, (long long)u); }
+  if (jkind == FDB_J_DENSE && ldJ < m) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "ldJ < m"); }
+  P->sp_kind = SP_BANDED;
+  P->jkind = jkind;
+  P->l = l;
+  P->u = u;
+  P->ldJ = ldJ;
+  P->j_len = jkind == FDB_J_BAND ? (l + u + 1) * n : ldJ * n;
+  I64View cv;
+  PLAN_TRY(setup_colors(P, colorvec, cv));
+  unsigned long long *d_cnt = nullptr;
+  PLAN_TRY(P->alloc_t(&d_cnt, std::max<int32_t>(P->C, 1)));
+  cudaMemset(d_cnt, 0, (size_t)std::max<int32_t>(P->C, 1) * 8);
+  if (n > 0 && P->C > 0) {
+    PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      count_band_colors<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, m, n, l, u, P->C, d_cnt);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+  }
+  std::vector<unsigned long long> cnt(std::max<int32_t>(P->C, 1), 0);
+  if (P->C > 0) cudaMemcpy(cnt.data(), d_cnt, (size_t)P->C * 8, cudaMemcpyDeviceToHost);
+  unsigned long long total = 0;
+  for (auto c : cnt) total += c;
+  P->E = (int64_t)total;
+  PLAN_TRY(finish_colored_plan(P, opts, cnt));
+  // SURVEY.md §8(d) banded: 8*sum_c band_len(c) written + 16*m*C read
+  P->alg_bytes = 8 * (int64_t)total + 16 * m * (int64_t)P->C;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "plan build: %s", cudaGetErrorString(e)); }
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, m, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  if (ldJ < m) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "ldJ < m"); }
+  P->sp_kind = SP_NONE;
+  P->jkind = FDB_J_DENSE;
+  P->ldJ = ldJ;
+  // contiguous column blocks per rank
+  const int64_t per = (n + P->world - 1) / P->world;
+  P->col_begin = std::min<int64_t>(n, per * P->rank);
+  P->col_end = std::min<int64_t>(n, P->col_begin + per);
+  const int64_t ncl = P->col_end - P->col_begin;
+  P->j_len = ldJ * ncl;
+  P->E = m * ncl;
+  P->C = (int32_t)n;
+  const bool central = P->fdtype == FDB_CENTRAL;
+  P->ldF = std::max<int64_t>(2, (m + 1) & ~(int64_t)1);
+  P->ldx = std::max<int64_t>(2, (n + 1) & ~(int64_t)1);
+  int64_t batch = (opts && opts->max_batch > 1) ? opts->max_batch : 1;
+  int64_t budget = (opts && opts->scratch_bytes > 0) ? opts->scratch_bytes : (int64_t)8 << 30;
+  const int64_t per_point = 8 * (P->ldx + P->ldF * (central ? 2 : 1));
+  batch = std::max<int64_t>(1, std::min<int64_t>(batch, budget / per_point));
+  batch = std::min<int64_t>(batch, std::max<int64_t>(ncl, 1));
+  batch = std::min<int64_t>(batch, 65535);   // gridDim.y of diff_columns
+  P->batch = batch;
+  P->slabs = batch;
+  P->n_groups = ncl == 0 ? 0 : (ncl + batch - 1) / batch;
+  PLAN_TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
+  PLAN_TRY(P->alloc_t(&P->Fp, (size_t)batch * P->ldF));
+  if (central) PLAN_TRY(P->alloc_t(&P->Fm, (size_t)batch * P->ldF));
+  PLAN_TRY(P->alloc_t(&P->xp, (size_t)batch * P->ldx));
+  PLAN_TRY(P->alloc_t(&P->eps_cols, (size_t)std::max<int64_t>(ncl, 1)));
+  // SURVEY.md §8(d) dense: 24*m per column
+  P->alg_bytes = 24 * m * ncl;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_destroy(fdb_plan *plan) {
+  free_plan(plan);
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
+  if (!P || !info) return fail(FDB_ERR_INVALID, "NULL argument");
+  memset(info, 0, sizeof *info);
+  info->m = P->m;
+  info->n = P->n;
+  info->n_entries = P->E;
+  info->j_len = P->j_len;
+  info->n_colors = P->C;
+  const int64_t n_local = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : (int64_t)P->local_colors.size();
+  info->n_local_colors = n_local;
+  info->n_groups = P->n_groups;
+  info->slabs = P->slabs;
+  info->fcalls_per_jacobian = P->fdtype == FDB_CENTRAL ? 2 * n_local : 1 + n_local;
+  info->device_bytes = (int64_t)P->device_bytes;
+  info->fdtype = P->fdtype;
+  info->jkind = P->jkind;
+  info->sp_kind = P->sp_kind;
+  info->color_bits = P->color_bits;
+  info->alg_bytes_scatter = P->alg_bytes;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_counters(const fdb_plan *P, fdb_counters_t *out) {
+  if (!P || !out) return fail(FDB_ERR_INVALID, "NULL argument");
+  *out = P->cnt;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_dense_range(const fdb_plan *P, int64_t *b, int64_t *e) {
+  if (!P || !b || !e) return fail(FDB_ERR_INVALID, "NULL argument");
+  *b = P->col_begin;
+  *e = P->col_end;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_color_owner(const fdb_plan *P, int32_t *owner_out, int64_t cap) {
+  if (!P || !owner_out) return fail(FDB_ERR_INVALID, "NULL argument");
+  if (P->sp_kind == SP_NONE) return fail(FDB_ERR_INVALID, "dense plans partition columns by range");
+  if (cap < (int64_t)P->owner.size()) return fail(FDB_ERR_INVALID, "owner_out too small");
+  std::copy(P->owner.begin(), P->owner.end(), owner_out);
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_get_eps(fdb_plan *P, double *h_eps, int64_t cap, void *stream) {
+  if (!P || !h_eps) return fail(FDB_ERR_INVALID, "NULL argument");
+  DeviceGuard g(P->device);
+  const int64_t count = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : P->C;
+  if (cap < count) return fail(FDB_ERR_INVALID, "h_eps too small (%lld < %lld)", (long long)cap, (long long)count);
+  const double *src = P->sp_kind == SP_NONE ? P->eps_cols : P->eps;
+  if (count > 0) {
+    CU(cudaMemcpyAsync(h_eps, src, (size_t)count * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_enable_timing(fdb_plan *P, int enable) {
+  if (!P) return fail(FDB_ERR_INVALID, "NULL plan");
+  P->timing = enable != 0;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_read_timing(fdb_plan *P, double *scatter_ms, int64_t *scatter_launches) {
+  if (!P || !scatter_ms || !scatter_launches) return fail(FDB_ERR_INVALID, "NULL argument");
+  DeviceGuard g(P->device);
+  double total = 0.0;
+  int64_t count = 0;
+  for (auto &ev : P->ev_pending) {
+    CU(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+    count += 1;
+    P->ev_pool.push_back(ev);
+  }
+  P->ev_pending.clear();
+  *scatter_ms = total;
+  *scatter_launches = count;
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_set_peers(fdb_plan *P, int n_peers, double *const *peer_J) {
+  if (!P) return fail(FDB_ERR_INVALID, "NULL plan");
+  if (n_peers < 0 || n_peers > 64) return fail(FDB_ERR_INVALID, "n_peers out of range");
+  if (P->sp_kind == SP_NONE || P->sp_kind == SP_BANDED)
+    return fail(FDB_ERR_UNSUPPORTED, "peer stores are implemented for the entry-driven (CSC / COO) scatters");
+  DeviceGuard g(P->device);
+  if (!P->d_peers) TRY(P->alloc_t(&P->d_peers, 64));
+  if (n_peers > 0) CU(cudaMemcpy(P->d_peers, peer_J, (size_t)n_peers * sizeof(double *), cudaMemcpyHostToDevice));
+  P->n_peers = n_peers;
+  return FDB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the hot path
+struct ScatterTimer {
+  fdb_plan *P;
+  cudaStream_t s;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  ScatterTimer(fdb_plan *p, cudaStream_t st) : P(p), s(st) {
+    if (!P->timing) return;
+    if (!P->ev_pool.empty()) { ev = P->ev_pool.back(); P->ev_pool.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, s);
+  }
+  ~ScatterTimer() {
+    if (!P->timing || !ev.first) return;
+    cudaEventRecord(ev.second, s);
+    P->ev_pending.push_back(ev);
+  }
+};
+
+static fdb_status call_f(fdb_plan *P, fdb_fn f, void *ctx, double *fx, const double *x, int64_t batch, cudaStream_t s) {
+  const int rc = f(ctx, fx, x, batch, P->ldF, P->ldx, (void *)s);
+  P->cnt.f_invocations += 1;
+  P->cnt.f_points += batch;
+  if (rc != 0) return fail(FDB_ERR_CALLBACK, "user f! returned %d", rc);
+  return FDB_OK;
+}
+
+template <typename CT>
+static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double absstep, double dir, cudaStream_t s) {
+  const int32_t C = P->C;
+  if (C <= 0) return FDB_OK;
+  const int central = P->fdtype == FDB_CENTRAL;
+  if (C <= kEpsRegColors) {
+    color_sumsq_reg<CT><<<P->eps_blocks, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, P->eps_chunk, P->partial);
+    finalize_eps<<<(C * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, kEpsRegColors, 0, C,
+                                                                      central, relstep, absstep, dir, P->eps, P->sumsq);
+    P->cnt.kernel_launches += 2;
+  } else {
+    for (int32_t k0 = 0; k0 < C; k0 += kEpsWindow) {
+      const int32_t W = std::min<int32_t>(kEpsWindow, C - k0);
+      const int32_t stride = std::min<int32_t>(C, kEpsWindow);
+      color_sumsq_win<CT><<<P->eps_blocks, kThreads, (size_t)kEpsWarps * W * sizeof(double), s>>>(
+          x, (const CT *)P->jcolor, P->n, P->eps_chunk, k0, W, P->partial);
+      // partial rows are W wide for this pass
+      finalize_eps<<<(W * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, W, k0, W, central,
+                                                                        relstep, absstep, dir, P->eps, P->sumsq);
+      (void)stride;
+      P->cnt.kernel_launches += 2;
+    }
+  }
+  CU(cudaGetLastError());
+  return FDB_OK;
+}
+
+template <typename CT, bool CENTRAL>
+static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x, double *J, double *fx,
+                              const double *f_in, double relstep, double absstep, double dir, cudaStream_t s) {
+  const int64_t n_local = (int64_t)P->local_colors.size();
+  // fill_matrix!(J, false)  jacobians.jl:530-532 — needed where the scatter does not define every slot itself
+  const bool ident = P->dest == nullptr && P->sp_kind != SP_BANDED;
+  const bool band_data = P->sp_kind == SP_BANDED && P->jkind == FDB_J_BAND;
+  // (identity / band-data launches define every slot this rank is responsible for, including zeros for columns without
+  //  a valid colour).  With peer buffers set the caller zero-fills J and synchronises the ranks BEFORE the call: a memset
+  //  here would race with the peers' stores.
+  const bool self_defining = (ident || band_data) && n_local > 0;
+  if (!self_defining && P->n_peers == 0 && P->j_len > 0) CU(cudaMemsetAsync(J, 0, (size_t)P->j_len * 8, s));
+  TRY(run_eps<CT>(P, x, relstep, absstep, dir, s));
+  const double *vfx = nullptr;
+  if (!CENTRAL) {
+    if (f_in) vfx = f_in;                                  // jacobians.jl:543-544
+    else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; } // :541-542
+  }
+  for (int64_t g = 0; g < P->n_groups; ++g) {
+    const int64_t l0 = g * P->slabs;
+    const int64_t G = std::min<int64_t>(P->slabs, n_local - l0);
+    for (int64_t b0 = 0; b0 < G; b0 += P->batch) {
+      const int64_t kc = std::min<int64_t>(P->batch, G - b0);
+      perturb_colors<CT, CENTRAL><<<P->grid(P->n), kThreads, 0, s>>>(
+          x, (const CT *)P->jcolor, P->eps, P->d_local_colors + l0 + b0, (int32_t)kc, P->C, P->no_drift ? 0 : 1, P->n,
+          P->ldx, P->xp, P->xm);
+      P->cnt.kernel_launches += 1;
+      TRY(call_f(P, f, ctx, P->Fp + b0 * P->ldF, P->xp, kc, s));               // f(fx1, x1)  :563 / :605
+      if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + b0 * P->ldF, P->xm, kc, s));   // f(fx, x)    :606
+    }
+    if (P->sp_kind == SP_BANDED) {
+      BandArgs a{};
+      a.jcolor = P->jcolor; a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps; a.local_of = P->local_of;
+      a.J = J; a.C = P->C; a.l0 = (int32_t)l0; a.G = (int32_t)G;
+      a.write_other = (g == 0 && P->rank == 0) ? 1 : 0;
+      a.to_dense = P->jkind == FDB_J_DENSE ? 1 : 0;
+      a.ldF = P->ldF; a.ldJ = P->ldJ; a.m = P->m; a.n = P->n; a.l = P->l; a.u = P->u;
+      const int64_t w = P->l + P->u + 1;
+      int64_t ntiles;
+      if (w >= 512) { a.chunks_per_col = (w + kThreads * 4 - 1) / (kThreads * 4); a.cols_per_tile = 0; ntiles = P->n * a.chunks_per_col; }
+      else { a.chunks_per_col = 0; a.cols_per_tile = std::max<int64_t>(1, 4096 / w); ntiles = (P->n + a.cols_per_tile - 1) / a.cols_per_tile; }
+      if (ntiles > 0) {
+        const int blocks = (int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16);
+        ScatterTimer tm(P, s);
+        diff_scatter_band<CT, CENTRAL><<<blocks, kThreads, 0, s>>>(a);
+        P->cnt.kernel_launches += 1;
+        P->cnt.scatter_launches += 1;
+      }
+    } else if (P->E > 0) {
+      ScatterArgs a{};
+      a.row = P->row32; a.ecolor = P->ecolor; a.dest = P->dest; a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps;
+      a.local_of = P->local_of; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers; a.C = P->C;
+      a.l0 = (int32_t)l0; a.G = (int32_t)G;
+      a.write_invalid_zero = (g == 0 && P->rank == 0 && P->has_invalid) ? 1 : 0;
+      a.ldF = P->ldF; a.E = P->E;
+      ScatterTimer tm(P, s);
+      if (ident) diff_scatter_ident<CT, CENTRAL><<<P->grid((P->E + kScatterVec - 1) / kScatterVec + 1), kThreads, 0, s>>>(a);
+      else diff_scatter_dest<CT, CENTRAL><<<P->grid(P->E), kThreads, 0, s>>>(a);
+      P->cnt.kernel_launches += 1;
+      P->cnt.scatter_launches += 1;
+    }
+  }
+  CU(cudaGetLastError());
+  return FDB_OK;
+}
+
+template <bool CENTRAL>
+static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, double *J, double *fx, const double *f_in,
+                            double relstep, double absstep, double dir, cudaStream_t s) {
+  const int64_t ncl = P->col_end - P->col_begin;
+  const double *vfx = nullptr;
+  if (!CENTRAL) {
+    if (f_in) vfx = f_in;
+    else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; }
+  }
+  if (ncl == 0) return FDB_OK;
+  component_eps<<<(int)((ncl + kThreads - 1) / kThreads), kThreads, 0, s>>>(x, P->col_begin, ncl, CENTRAL ? 1 : 0, relstep,
+                                                                          absstep, dir, P->eps_cols);
+  const int32_t B = (int32_t)P->batch;
+  replicate_x<<<P->grid(P->n), kThreads, 0, s>>>(x, P->n, P->ldx, B, P->xp);
+  P->cnt.kernel_launches += 2;
+  int64_t prev_c0 = 0;
+  int32_t prevB = 0;
+  for (int64_t c0l = 0; c0l < ncl; c0l += B) {
+    const int32_t kc = (int32_t)std::min<int64_t>(B, ncl - c0l);
+    const int64_t c0 = P->col_begin + c0l;
+    const int sb = (std::max(kc, prevB) + kThreads - 1) / kThreads;
+    set_components<<<sb, kThreads, 0, s>>>(x, P->eps_cols, c0l, c0, prev_c0, kc, prevB, P->ldx, 1.0, P->xp);
+    TRY(call_f(P, f, ctx, P->Fp, P->xp, kc, s));                         // f(fx1, x1)   jacobians.jl:553 / :594
+    if (CENTRAL) {
+      set_components<<<sb, kThreads, 0, s>>>(x, P->eps_cols, c0l, c0, 0, kc, 0, P->ldx, -1.0, P->xp);
+      TRY(call_f(P, f, ctx, P->Fm, P->xp, kc, s));                       // f(fx, x1)    :596
+      P->cnt.kernel_launches += 1;
+    }
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((P->m + kThreads * 4 - 1) / (kThreads * 4), (int64_t)P->sm_count * 8 / kc + 1));
+    dim3 grid((unsigned)gx, (unsigned)kc);
+    {
+      ScatterTimer tm(P, s);
+      diff_columns<CENTRAL><<<grid, kThreads, 0, s>>>(P->Fp, CENTRAL ? P->Fm : vfx, P->eps_cols, c0l, kc, P->m, P->ldF, P->ldJ,
+                                                      J + c0l * P->ldJ);
+    }
+    P->cnt.kernel_launches += 2;
+    P->cnt.scatter_launches += 1;
+    prev_c0 = c0;
+    prevB = kc;
+  }
+  CU(cudaGetLastError());
+  return FDB_OK;
+}
+
+extern "C" {
+
+fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, double *d_J, double *d_fx,
+                        const double *d_f_in, double relstep, double absstep, double dir, void *stream) {
+  if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
+  if ((P->n > 0 && !d_x) || (P->j_len > 0 && !d_J)) return fail(FDB_ERR_INVALID, "NULL x or J");
+  DeviceGuard g(P->device);
+  if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  // jacobians.jl:508-509 defaults
+  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);
+  if (!(absstep > 0)) absstep = relstep;
+  double *fx = d_fx ? d_fx : P->fx_own;
+  fdb_status st;
+  if (P->sp_kind == SP_NONE) {
+    st = P->fdtype == FDB_CENTRAL ? run_dense<true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
+                                  : run_dense<false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+  } else {
+    st = dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      return P->fdtype == FDB_CENTRAL
+                 ? run_colored<CT, true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
+                 : run_colored<CT, false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    });
+  }
+  if (st == FDB_OK) P->cnt.jacobians += 1;
+  return st;
+}
+
+fdb_status fdb_jacobian_host(fdb_plan *P, fdb_fn f, void *ctx, const double *h_x, double *h_J, double *h_fx,
+                             const double *h_f_in, double relstep, double absstep, double dir) {
+  if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
+  if ((P->n > 0 && !h_x) || (P->j_len > 0 && !h_J)) return fail(FDB_ERR_INVALID, "NULL x or J");
+  DeviceGuard g(P->device);
+  if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
+  if (!P->hstream) {
+    CU(cudaStreamCreateWithFlags(&P->hstream, cudaStreamNonBlocking));
+    TRY(P->alloc_t(&P->h_dx, (size_t)std::max<int64_t>(P->n, 1)));
+    TRY(P->alloc_t(&P->h_dJ, (size_t)std::max<int64_t>(P->j_len, 1)));
+    TRY(P->alloc_t(&P->h_dfx, (size_t)P->ldF));
+    TRY(P->alloc_t(&P->h_dfin, (size_t)P->ldF));
+  }
+  cudaStream_t s = P->hstream;
+  if (P->n > 0) CU(cudaMemcpyAsync(P->h_dx, h_x, (size_t)P->n * 8, cudaMemcpyHostToDevice, s));
+  const double *fin = nullptr;
+  if (h_f_in && P->fdtype == FDB_FORWARD) {
+    CU(cudaMemcpyAsync(P->h_dfin, h_f_in, (size_t)P->m * 8, cudaMemcpyHostToDevice, s));
+    fin = P->h_dfin;
+  }
+  fdb_status st = fdb_jacobian(P, f, ctx, P->h_dx, P->h_dJ, P->h_dfx, fin, relstep, absstep, dir, (void *)s);
+  if (st != FDB_OK) { cudaStreamSynchronize(s); return st; }
+  if (P->j_len > 0) CU(cudaMemcpyAsync(h_J, P->h_dJ, (size_t)P->j_len * 8, cudaMemcpyDeviceToHost, s));
+  if (h_fx && P->fdtype == FDB_FORWARD && !fin && P->m > 0)
+    CU(cudaMemcpyAsync(h_fx, P->h_dfx, (size_t)P->m * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return FDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+fdb_status fdb_host_alloc(void **p, size_t bytes) {
+  if (!p) return fail(FDB_ERR_INVALID, "NULL argument");
+  CU(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault));
+  return FDB_OK;
+}
+fdb_status fdb_host_free(void *p) { if (p) CU(cudaFreeHost(p)); return FDB_OK; }
+fdb_status fdb_device_alloc(void **p, size_t bytes) {
+  if (!p) return fail(FDB_ERR_INVALID, "NULL argument");
+  CU(cudaMalloc(p, bytes ? bytes : 16));
+  return FDB_OK;
+}
+fdb_status fdb_device_free(void *p) { if (p) CU(cudaFree(p)); return FDB_OK; }
+fdb_status fdb_memcpy_h2d(void *d, const void *h, size_t bytes, void *stream) {
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return FDB_OK;
+}
+fdb_status fdb_memcpy_d2h(void *h, const void *d, size_t bytes, void *stream) {
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return FDB_OK;
+}
+fdb_status fdb_stream_sync(void *stream) { CU(cudaStreamSynchronize((cudaStream_t)stream)); return FDB_OK; }
+
+fdb_status fdb_ipc_get_handle(void *d_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, 64);
+  return FDB_OK;
+}
+fdb_status fdb_ipc_open(const unsigned char handle[64], void **d_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FDB_OK;
+}
+fdb_status fdb_ipc_close(void *d_ptr) { CU(cudaIpcCloseMemHandle(d_ptr)); return FDB_OK; }
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// kernels_eps.cuh — K2: step size per colour, on device, no host sync.
+//
+// Reference (per colour k, jacobians.jl:559-561 / :600-602):
+//     @. x2 = x1 * (_color == k);  tmp = norm(x2);  eps = compute_epsilon(Val(fd), sqrt(tmp), relstep, absstep, dir)
+// i.e. eps_k = max(relstep*|sqrt(||x[color==k]||_2)|, absstep) [*dir forward] (epsilons.jl:26-29,50-53).
+// The colour-k components of x1 are still pristine when colour k is processed (every component belongs to
+// exactly one colour), so all C sums of squares come from ONE pass over (x, colour) instead of C passes.
+//
+// Determinism: fixed block ranges, fixed in-block order, fixed cross-block order — no floating-point atomics.
+#pragma once
+#include "common.cuh"
+
+namespace fdb {
+
+constexpr int kEpsRegColors = 8;     // register path when C <= 8
+constexpr int kEpsWindow = 512;      // colours per pass on the shared-memory path
+constexpr int kEpsWarps = kThreads / 32;
+
+// C <= 8: per-thread register accumulators, shuffle tree, fixed warp order.
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int64_t chunk,
+                double *__restrict__ partial /* [gridDim.x][kEpsRegColors] */) {
+  const int64_t start = (int64_t)blockIdx.x * chunk;
+  int64_t end = start + chunk;
+  if (end > n) end = n;
+  double acc[kEpsRegColors];
+#pragma unroll
+  for (int k = 0; k < kEpsRegColors; ++k) acc[k] = 0.0;
+  for (int64_t j = start + threadIdx.x; j < end; j += kThreads) {
+    const double v = x[j];
+    const uint32_t c = (uint32_t)jcolor[j];
+    const double sq = v * v;
+#pragma unroll
+    for (int k = 0; k < kEpsRegColors; ++k) acc[k] += (c == (uint32_t)k) ? sq : 0.0;
+  }
+  __shared__ double s[kEpsWarps][kEpsRegColors];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kEpsRegColors; ++k) {
+    const double t = warp_sum(acc[k]);
+    if (lane == 0) s[w][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kEpsRegColors) {
+    double t = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kEpsWarps; ++ww) t += s[ww][threadIdx.x];
+    partial[(int64_t)blockIdx.x * kEpsRegColors + threadIdx.x] = t;
+  }
+}
+
+// General C: colours [k0, k0+W) per pass; every warp owns a private W-entry accumulator in shared memory, lanes that
+// hold the same colour are combined in ascending lane order (match.any), the lowest lane adds into the warp's slot.
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+color_sumsq_win(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int64_t chunk, int32_t k0,
+                int32_t W, double *__restrict__ partial /* [gridDim.x][W] */) {
+  extern __shared__ double sacc[];  // kEpsWarps * W
+  for (int i = threadIdx.x; i < kEpsWarps * W; i += kThreads) sacc[i] = 0.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double *acc = sacc + (size_t)w * W;
+  const int64_t start = (int64_t)blockIdx.x * chunk;
+  int64_t end = start + chunk;
+  if (end > n) end = n;
+  // warp w walks the block's range in 32-wide steps: step t covers [start + (t*kEpsWarps + w)*32, +32)
+  for (int64_t base = start + (int64_t)w * 32; base < end; base += (int64_t)kEpsWarps * 32) {
+    const int64_t j = base + lane;
+    int32_t c = -1;
+    double sq = 0.0;
+    if (j < end) {
+      const double v = x[j];
+      sq = v * v;
+      const int32_t cc = (int32_t)(uint32_t)jcolor[j] - k0;
+      if (cc >= 0 && cc < W) c = cc;
+    }
+    const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+    if (c >= 0) {
+      const unsigned peers = __match_any_sync(act, c);
+      double s = 0.0;
+      unsigned mm = peers;
+      while (mm) {
+        const int l = __ffs(mm) - 1;
+        mm &= mm - 1;
+        s += __shfl_sync(peers, sq, l);
+      }
+      if (lane == __ffs(peers) - 1) acc[c] += s;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W; i += kThreads) {
+    double t = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < kEpsWarps; ++ww) t += sacc[(size_t)ww * W + i];
+    partial[(int64_t)blockIdx.x * W + i] = t;
+  }
+}
+
+// One warp per colour: fixed-order reduction over the block partials, then the step-size formula.
+__global__ void __launch_bounds__(kThreads)
+finalize_eps(const double *__restrict__ partial, int32_t nblocks, int32_t stride /* colours per partial row */,
+             int32_t k0, int32_t ncolors_here, int fdtype_central, double relstep, double absstep, double dir,
+             double *__restrict__ eps /* [C] */, double *__restrict__ sumsq /* [C] or null */) {
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5);
+  if (c >= ncolors_here) return;
+  double t = 0.0;
+  for (int b = lane; b < nblocks; b += 32) t += partial[(int64_t)b * stride + c];
+  t = warp_sum(t);
+  if (lane == 0) {
+    const double tmp = sqrt(t);                      // norm(x2)                     jacobians.jl:560
+    const double a = relstep * fabs(sqrt(tmp));      // relstep*abs(sqrt(tmp))       :561 + epsilons.jl:28
+    double e = a > absstep ? a : absstep;            // max(.., absstep)
+    if (!fdtype_central) e = e * dir;                // *dir (forward only)          epsilons.jl:28 vs :52
+    eps[k0 + c] = e;
+    if (sumsq) sumsq[k0 + c] = t;
+  }
+}
+
+// Dense-column branch: per-COMPONENT step (jacobians.jl:550,592): eps_i = compute_epsilon(fd, x_i, relstep, absstep, dir)
+__global__ void __launch_bounds__(kThreads)
+component_eps(const double *__restrict__ x, int64_t c0, int64_t ncols, int fdtype_central, double relstep,
+              double absstep, double dir, double *__restrict__ eps) {
+  const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (i >= ncols) return;
+  const double a = relstep * fabs(x[c0 + i]);
+  double e = a > absstep ? a : absstep;
+  if (!fdtype_central) e = e * dir;
+  eps[i] = e;
+}
+
+}  // namespace fdb

@@ -1,0 +1,179 @@
+// kernels_plan.cuh — plan-time device kernels: validate the caller's Int64 1-based index arrays and build the
+// compressed per-entry streams the hot kernels read (0-based int32 rows, narrow colour ids, destination offsets).
+// This replaces the per-call index work of the reference's prologue (jacobians.jl:515-535: reshape of colorvec,
+// findstructralnz / _findstructralnz, the O(n+nnz) same-pattern comparison of ext/FiniteDiffSparseArraysExt.jl:51-52)
+// — done once per (pattern, colorvec), on the device, instead of on every Jacobian.
+#pragma once
+#include "common.cuh"
+
+namespace fdb {
+
+enum PlanErr : uint32_t {
+  kErrColptr = 1u,        // colptr not monotone / wrong ends
+  kErrRowRange = 2u,      // row index outside 1..m
+  kErrColRange = 4u,      // column index outside 1..n
+  kErrSlotRange = 8u,     // slot outside 1..j_len
+  kErrPatternDiff = 16u,  // J pattern != sparsity pattern (informational)
+  kErrMissingInJ = 32u,   // sparsity entry absent from J's pattern (setindex! would have to insert)
+  kErrRowOrder = 64u      // rows within a column not strictly increasing (binary search needs it)
+};
+
+// max / min of colorvec
+__global__ void __launch_bounds__(kThreads)
+color_minmax(const int64_t *__restrict__ colorvec, int64_t n, long long *__restrict__ out_max,
+             long long *__restrict__ out_min) {
+  long long mx = LLONG_MIN, mn = LLONG_MAX;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += stride) {
+    const long long c = colorvec[j];
+    mx = c > mx ? c : mx;
+    mn = c < mn ? c : mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, mx, o), b = __shfl_xor_sync(0xffffffffu, mn, o);
+    mx = a > mx ? a : mx;
+    mn = b < mn ? b : mn;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out_max, mx);
+    atomicMin(out_min, mn);
+  }
+}
+
+// jcolor[j] = colorvec[j]-1 (or j for the default 1:n), invalid marker for colorvec[j] < 1
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+convert_colors(const int64_t *__restrict__ colorvec /* null => 1:n */, int64_t n, CT *__restrict__ jcolor) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += stride) {
+    const int64_t c = colorvec ? colorvec[j] : j + 1;
+    jcolor[j] = c >= 1 ? (CT)(c - 1) : (CT)ColorTraits<CT>::invalid;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+validate_colptr(const int64_t *__restrict__ colptr, int64_t n, int64_t nnz, uint32_t *__restrict__ err) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = blockIdx.x * (int64_t)kThreads + threadIdx.x; c <= n; c += stride) {
+    bool bad = false;
+    if (c == 0 && colptr[0] != 1) bad = true;
+    if (c == n && colptr[n] != nnz + 1) bad = true;
+    if (c < n && colptr[c + 1] < colptr[c]) bad = true;
+    if (bad) atomicOr(err, kErrColptr);
+  }
+}
+
+// column (0-based) of CSC slot p (0-based): largest c with colptr[c]-1 <= p
+__device__ __forceinline__ int64_t csc_col_of(const int64_t *__restrict__ colptr, int64_t n, int64_t p) {
+  int64_t lo = 0, hi = n;  // invariant: colptr[lo]-1 <= p < colptr[hi]-1
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (colptr[mid] - 1 <= p) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// For every CSC slot p: row32[p], ecolor[p] (colour of its column), optional col32[p]; per-colour entry counts.
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+expand_csc(const int64_t *__restrict__ colptr, const int64_t *__restrict__ rowval, int64_t m, int64_t n, int64_t nnz,
+           const CT *__restrict__ jcolor, int32_t C, int32_t *__restrict__ row32, CT *__restrict__ ecolor,
+           int32_t *__restrict__ col32 /* nullable */, unsigned long long *__restrict__ color_count /* [C] nullable */,
+           uint32_t *__restrict__ err) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < nnz; p += stride) {
+    const int64_t c = csc_col_of(colptr, n, p);
+    const int64_t r = rowval[p];
+    if (r < 1 || r > m) { atomicOr(err, kErrRowRange); row32[p] = 0; }
+    else row32[p] = (int32_t)(r - 1);
+    if (p > colptr[c] - 1 && rowval[p - 1] >= r) atomicOr(err, kErrRowOrder);
+    const CT k = jcolor[c];
+    ecolor[p] = k;
+    if (col32) col32[p] = (int32_t)c;
+    if (color_count && (uint32_t)k < (uint32_t)C) atomicAdd(color_count + (uint32_t)k, 1ull);
+  }
+}
+
+// same-pattern test of ext/FiniteDiffSparseArraysExt.jl:51-52:  J.colptr == sp.colptr && J.rowval == sp.rowval
+__global__ void __launch_bounds__(kThreads)
+compare_i64(const int64_t *__restrict__ a, const int64_t *__restrict__ b, int64_t count, uint32_t *__restrict__ err) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  bool diff = false;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < count; i += stride) diff |= a[i] != b[i];
+  if (diff) atomicOr(err, kErrPatternDiff);
+}
+
+// dest[p] = col*ldJ + row  (dense column-major J)
+__global__ void __launch_bounds__(kThreads)
+dest_dense_from_rc(const int32_t *__restrict__ row32, const int32_t *__restrict__ col32, int64_t E, int64_t ldJ,
+                   int64_t *__restrict__ dest) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < E; e += stride)
+    dest[e] = (int64_t)col32[e] * ldJ + row32[e];
+}
+
+// dest[p] = slot of (row,col) in another CSC pattern (J[r,c] = v on a SparseMatrixCSC: binary search in the column)
+__global__ void __launch_bounds__(kThreads)
+dest_other_csc(const int32_t *__restrict__ row32, const int32_t *__restrict__ col32, int64_t E,
+               const int64_t *__restrict__ j_colptr, const int64_t *__restrict__ j_rowval, int64_t *__restrict__ dest,
+               uint32_t *__restrict__ err) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < E; e += stride) {
+    const int64_t c = col32[e], r = (int64_t)row32[e] + 1;
+    int64_t lo = j_colptr[c] - 1, hi = j_colptr[c + 1] - 1;  // [lo,hi)
+    int64_t found = -1;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int64_t rv = j_rowval[mid];
+      if (rv == r) { found = mid; break; }
+      if (rv < r) lo = mid + 1; else hi = mid;
+    }
+    if (found < 0) { atomicOr(err, kErrMissingInJ); found = 0; }
+    dest[e] = found;
+  }
+}
+
+// COO entries (rows_index/cols_index, 1-based): row32, ecolor, dest (dense or explicit slots), validation, counts
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+prepare_coo(const int64_t *__restrict__ rows, const int64_t *__restrict__ cols, const int64_t *__restrict__ slots,
+            int64_t nnz, int64_t m, int64_t n, int64_t ldJ, int64_t j_len, const CT *__restrict__ jcolor, int32_t C,
+            int32_t *__restrict__ row32, CT *__restrict__ ecolor, int64_t *__restrict__ dest,
+            unsigned long long *__restrict__ color_count, uint32_t *__restrict__ err) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < nnz; e += stride) {
+    int64_t r = rows[e], c = cols[e];
+    if (r < 1 || r > m) { atomicOr(err, kErrRowRange); r = 1; }
+    if (c < 1 || c > n) { atomicOr(err, kErrColRange); c = 1; }
+    row32[e] = (int32_t)(r - 1);
+    const CT k = jcolor[c - 1];
+    ecolor[e] = k;
+    int64_t d;
+    if (slots) {
+      d = slots[e] - 1;
+      if (d < 0 || d >= j_len) { atomicOr(err, kErrSlotRange); d = 0; }
+    } else {
+      d = (c - 1) * ldJ + (r - 1);
+    }
+    dest[e] = d;
+    if (color_count && (uint32_t)k < (uint32_t)C) atomicAdd(color_count + (uint32_t)k, 1ull);
+  }
+}
+
+// per-colour column counts (banded plans: entries per colour = sum of band lengths of its columns)
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+count_band_colors(const CT *__restrict__ jcolor, int64_t m, int64_t n, int64_t l, int64_t u, int32_t C,
+                  unsigned long long *__restrict__ color_count) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = blockIdx.x * (int64_t)kThreads + threadIdx.x; c < n; c += stride) {
+    const uint32_t k = (uint32_t)jcolor[c];
+    if (k >= (uint32_t)C) continue;
+    int64_t r_lo = c - u; if (r_lo < 0) r_lo = 0;
+    int64_t r_hi = c + l; if (r_hi > m - 1) r_hi = m - 1;
+    if (r_hi >= r_lo) atomicAdd(color_count + k, (unsigned long long)(r_hi - r_lo + 1));
+  }
+}
+
+}  // namespace fdb

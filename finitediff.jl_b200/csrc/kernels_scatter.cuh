@@ -1,0 +1,277 @@
+// kernels_scatter.cuh — K5: the fused divided-difference + decompression ("diff+scatter") kernels.
+//
+// Reference, per colour k (jacobians.jl:565-572 / :607-614):
+//     @. vfx1 = (vfx1 - vfx) / eps_k            (a full-length pass, in place)
+//     _colorediteration!(J, ..., vfx1, colorvec, k, n)   -> for every structural entry (r,c) with colorvec[c]==k:
+//                                                           J[r,c] = vfx1[r]
+// (CSC same-pattern: ext/FiniteDiffSparseArraysExt.jl:38-47; CSC->J[r,c]: :20-28; COO: src/iteration_utils.jl:25-32;
+//  banded whole-band: ext/FiniteDiffBandedMatricesExt.jl:13-27; dense column: jacobians.jl:555,597.)
+//
+// B200 formulation: the f! outputs of the colours of a group stay resident as slabs F[slab][m]; ONE launch walks J's
+// value storage in storage order, and for every structural entry e (row r_e, colour k_e) computes
+//     J[dest(e)] = (F[slab(k_e)][r_e] - fx[r_e]) / eps[k_e]          (central: (Fp - Fm) / (2 eps))
+// at gather time — the divided difference is never materialised, index/colour streams are read once, fully
+// coalesced, and J is written once with full sectors (per-colour launches would touch every sector of nzval C times).
+// IEEE subtraction and division are the same operations the reference performs, so values are bit-identical
+// given the same f! outputs and eps.
+#pragma once
+#include "common.cuh"
+
+namespace fdb {
+
+constexpr int kScatterVec = 4;         // entries per thread per step (int4 row load, 2 x 16 B stores)
+constexpr int kSmemTable = 2048;       // colours whose (slab, eps) tables are staged in shared memory
+
+struct ScatterArgs {
+  const int32_t *row;        // [E] 0-based row of entry e
+  const void *ecolor;        // [E] 0-based colour of the entry's column (CT)
+  const int64_t *dest;       // [E] destination offset, or null => identity (nzval[e])
+  const double *fx;          // forward: vfx = f(x) [m]; central: unused
+  const double *Fp;          // slabs [G][ldF]: f(x + eps_k e_k)
+  const double *Fm;          // central: slabs f(x - eps_k e_k)
+  const double *eps;         // [C]
+  const int32_t *local_of;   // [C] colour -> local index on this rank, -1 if not owned
+  double *J;
+  double *const *peers;      // optional peer J buffers (multi-GPU fused gather), device array
+  int32_t n_peers;
+  int32_t C;
+  int32_t l0, G;             // this launch covers local colours [l0, l0+G)
+  int32_t write_invalid_zero;// entries whose column has no valid colour get 0 (fill_matrix! semantics)
+  int64_t ldF;
+  int64_t E;
+};
+
+template <typename CT, bool CENTRAL>
+__device__ __forceinline__ bool entry_value(const ScatterArgs &a, const int32_t *s_slab, const double *s_eps,
+                                            bool use_smem, int32_t r, uint32_t k, double &v) {
+  if (k >= (uint32_t)a.C) { v = 0.0; return a.write_invalid_zero != 0; }
+  int32_t slab;
+  double e;
+  if (use_smem) { slab = s_slab[k]; e = s_eps[k]; }
+  else { slab = __ldg(a.local_of + k) - a.l0; e = __ldg(a.eps + k); if (__ldg(a.local_of + k) < 0) slab = -1; }
+  if (slab < 0 || slab >= a.G) return false;
+  const double hi = __ldg(a.Fp + (int64_t)slab * a.ldF + r);
+  if (CENTRAL) {
+    const double lo = __ldg(a.Fm + (int64_t)slab * a.ldF + r);
+    v = (hi - lo) / (2 * e);                       // jacobians.jl:607  (vfx1 - vfx) / 2epsilon
+  } else {
+    const double lo = __ldg(a.fx + r);
+    v = (hi - lo) / e;                             // jacobians.jl:565  (vfx1 - vfx) / epsilon
+  }
+  return true;
+}
+
+__device__ __forceinline__ void store_peers(const ScatterArgs &a, int64_t off, double v) {
+  for (int p = 0; p < a.n_peers; ++p) a.peers[p][off] = v;
+}
+
+// Identity destination (CSC nzval, same pattern).  4 entries per thread per step; vector loads of the row / colour
+// streams, 16-byte stores when all 4 entries belong to this launch.
+template <typename CT, bool CENTRAL>
+__global__ void __launch_bounds__(kThreads)
+diff_scatter_ident(const ScatterArgs a) {
+  __shared__ int32_t s_slab[kSmemTable];
+  __shared__ double s_eps[kSmemTable];
+  const bool use_smem = a.C <= kSmemTable;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < a.C; i += kThreads) {
+      const int32_t lo = a.local_of[i];
+      s_slab[i] = lo < 0 ? -1 : lo - a.l0;
+      s_eps[i] = a.eps[i];
+    }
+    __syncthreads();
+  }
+  const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
+  const int64_t nvec = a.E / kScatterVec;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.J) & 15) == 0) && a.n_peers == 0;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < nvec; i += stride) {
+    const int64_t e0 = i * kScatterVec;
+    const int4 r4 = __ldcs(reinterpret_cast<const int4 *>(a.row) + i);
+    uint32_t k[4];
+    if (sizeof(CT) == 1) {
+      const uint32_t pk = __ldcs(reinterpret_cast<const uint32_t *>(ecolor) + i);
+      k[0] = pk & 0xFF; k[1] = (pk >> 8) & 0xFF; k[2] = (pk >> 16) & 0xFF; k[3] = pk >> 24;
+    } else if (sizeof(CT) == 2) {
+      const uint2 pk = __ldcs(reinterpret_cast<const uint2 *>(ecolor) + i);
+      k[0] = pk.x & 0xFFFF; k[1] = pk.x >> 16; k[2] = pk.y & 0xFFFF; k[3] = pk.y >> 16;
+    } else {
+      const int4 pk = __ldcs(reinterpret_cast<const int4 *>(ecolor) + i);
+      k[0] = (uint32_t)pk.x; k[1] = (uint32_t)pk.y; k[2] = (uint32_t)pk.z; k[3] = (uint32_t)pk.w;
+    }
+    const int32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
+    double v[4];
+    bool w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) w[t] = entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, r[t], k[t], v[t]);
+    if (vec_ok && w[0] && w[1] && w[2] && w[3]) {
+      double2 *out = reinterpret_cast<double2 *>(a.J + e0);
+      __stcs(out, make_double2(v[0], v[1]));
+      __stcs(out + 1, make_double2(v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (w[t]) { a.J[e0 + t] = v[t]; store_peers(a, e0 + t, v[t]); }
+    }
+  }
+  // tail (E % 4 entries)
+  const int64_t tail0 = nvec * kScatterVec;
+  const int64_t gi = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (gi < a.E - tail0) {
+    const int64_t e = tail0 + gi;
+    double v;
+    if (entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, a.row[e], (uint32_t)ecolor[e], v)) {
+      a.J[e] = v;
+      store_peers(a, e, v);
+    }
+  }
+}
+
+// Explicit destination per entry (CSC sparsity -> dense / other-pattern CSC J, COO -> dense J or slots).
+template <typename CT, bool CENTRAL>
+__global__ void __launch_bounds__(kThreads)
+diff_scatter_dest(const ScatterArgs a) {
+  __shared__ int32_t s_slab[kSmemTable];
+  __shared__ double s_eps[kSmemTable];
+  const bool use_smem = a.C <= kSmemTable;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < a.C; i += kThreads) {
+      const int32_t lo = a.local_of[i];
+      s_slab[i] = lo < 0 ? -1 : lo - a.l0;
+      s_eps[i] = a.eps[i];
+    }
+    __syncthreads();
+  }
+  const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < a.E; e += stride) {
+    double v;
+    // no zero-writes here: J was zero-filled (fill_matrix!) before the first group
+    const uint32_t k = (uint32_t)ecolor[e];
+    if (k < (uint32_t)a.C && entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, __ldcs(a.row + e), k, v)) {
+      const int64_t d = __ldcs(a.dest + e);
+      a.J[d] = v;
+      store_peers(a, d, v);
+    }
+  }
+}
+
+// ---- banded: ext/FiniteDiffBandedMatricesExt.jl:13-27 ----
+// Every in-band (r,c), r in [max(1,c-u), min(m,c+l)], receives vfx[r] of column c's colour: the destination is the
+// contiguous band column data[:,c] (slot u+r-c, 0-based) and the source rows are contiguous too, so this is a
+// pure streaming transform: coalesced gather from the (L2-resident) slab, coalesced full-sector stores.
+struct BandArgs {
+  const void *jcolor;        // [n] colour of column c (CT)
+  const double *fx, *Fp, *Fm, *eps;
+  const int32_t *local_of;
+  double *J;
+  int32_t C, l0, G;
+  int32_t write_other;       // first launch / single group: also define slots this launch does not own (0)
+  int32_t to_dense;          // 1: J is dense column-major (ldJ), only in-matrix slots are written
+  int64_t ldF, ldJ;
+  int64_t m, n, l, u;
+  int64_t cols_per_tile, chunks_per_col;   // tiling of the (l+u+1) x n band
+};
+
+template <typename CT, bool CENTRAL>
+__global__ void __launch_bounds__(kThreads)
+diff_scatter_band(const BandArgs a) {
+  const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
+  const int64_t w = a.l + a.u + 1;
+  if (a.chunks_per_col > 0) {
+    // wide band: one tile = kThreads*4 consecutive slots of one column
+    const int64_t ntiles = a.n * a.chunks_per_col;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t c = tile / a.chunks_per_col;
+      const int64_t d0 = (tile - c * a.chunks_per_col) * (kThreads * 4);
+      const uint32_t k = (uint32_t)jcolor[c];
+      int32_t slab = -1;
+      double e = 1.0;
+      if (k < (uint32_t)a.C) {
+        const int32_t lo = __ldg(a.local_of + k);
+        slab = lo < 0 ? -1 : lo - a.l0;
+        if (slab >= a.G) slab = -1;
+        e = __ldg(a.eps + k);
+      }
+      const bool owned = slab >= 0;
+      const bool zero_col = k >= (uint32_t)a.C && a.write_other && !a.to_dense;  // no valid colour: stays 0 (fill_matrix!)
+      if (!owned && !zero_col) continue;   // a column of another group / rank: not ours to write
+      const double denom = CENTRAL ? 2 * e : e;
+      const double *hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF;
+      const double *lo = CENTRAL ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t d = d0 + t * kThreads + threadIdx.x;
+        if (d >= w) break;
+        const int64_t r = c + d - a.u;
+        const bool in = r >= 0 && r < a.m;
+        double v = 0.0;
+        if (owned && in) v = (__ldg(hi + r) - __ldg(lo + r)) / denom;
+        if (a.to_dense) {
+          if (owned && in) a.J[c * a.ldJ + r] = v;
+        } else {
+          st_stream(a.J + c * w + d, v);   // corner slots outside the matrix get 0
+        }
+      }
+    }
+  } else {
+    // narrow band: a tile = cols_per_tile whole columns, flat index inside the tile
+    const int64_t ntiles = (a.n + a.cols_per_tile - 1) / a.cols_per_tile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t c0 = tile * a.cols_per_tile;
+      int64_t ncol = a.n - c0;
+      if (ncol > a.cols_per_tile) ncol = a.cols_per_tile;
+      const int32_t total = (int32_t)(ncol * w);
+      const int32_t w32 = (int32_t)w;
+      for (int32_t t = threadIdx.x; t < total; t += kThreads) {
+        const int32_t cc = t / w32;
+        const int32_t d = t - cc * w32;
+        const int64_t c = c0 + cc;
+        const int64_t r = c + d - a.u;
+        const bool in = r >= 0 && r < a.m;
+        const uint32_t k = (uint32_t)jcolor[c];
+        int32_t slab = -1;
+        double e = 1.0;
+        if (k < (uint32_t)a.C) {
+          const int32_t lo = __ldg(a.local_of + k);
+          slab = lo < 0 ? -1 : lo - a.l0;
+          if (slab >= a.G) slab = -1;
+          e = __ldg(a.eps + k);
+        }
+        double v = 0.0;
+        if (in && slab >= 0) {
+          const double hi = __ldg(a.Fp + (int64_t)slab * a.ldF + r);
+          const double lo = CENTRAL ? __ldg(a.Fm + (int64_t)slab * a.ldF + r) : __ldg(a.fx + r);
+          v = (hi - lo) / (CENTRAL ? 2 * e : e);
+        }
+        if (a.to_dense) {
+          if (in && slab >= 0) a.J[c * a.ldJ + r] = v;
+        } else if (slab >= 0) {
+          a.J[c0 * w + t] = v;                       // owned column: whole data column (corner slots get 0)
+        } else if (a.write_other && k >= (uint32_t)a.C) {
+          a.J[c0 * w + t] = 0.0;                     // column without a valid colour: stays zero (fill_matrix!)
+        }
+      }
+    }
+  }
+}
+
+// ---- dense column branch: J[:, c] = (fx1 - fx)/eps_c  (jacobians.jl:555) or (fx1 - fx_minus)/(2 eps_c) (:597) ----
+template <bool CENTRAL>
+__global__ void __launch_bounds__(kThreads)
+diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx, const double *__restrict__ eps_local,
+             int64_t col0_local, int32_t B, int64_t m, int64_t ldF, int64_t ldJ, double *__restrict__ Jcols) {
+  // grid.y = column within the batch, grid.x strides over rows
+  const int b = blockIdx.y;
+  if (b >= B) return;
+  const double e = eps_local[col0_local + b];
+  const double denom = CENTRAL ? 2 * e : e;
+  const double *hi = Fp + (int64_t)b * ldF;
+  const double *lo = CENTRAL ? Fm_or_fx + (int64_t)b * ldF : Fm_or_fx;
+  double *out = Jcols + (int64_t)b * ldJ;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < m; i += stride)
+    st_stream(out + i, (ld_stream(hi + i) - __ldg(lo + i)) / denom);
+}
+
+}  // namespace fdb
