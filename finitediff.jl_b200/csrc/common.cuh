@@ -16,9 +16,35 @@ template <> struct ColorTraits<int32_t>  { static constexpr uint32_t invalid = 0
 
 constexpr int kThreads = 256;
 
-// streaming (read-once) loads / stores: keep L1 for the gathered vectors
+// Streaming kernels walk their data in tiles of kTile consecutive elements per block step.  Lane t of the block owns
+// the element PAIRS (tile + 2t, tile + 2t + 1) and (tile + kTile/2 + 2t, ...): every warp-level access is one
+// contiguous run (512 B for a double2, 64..256 B for the index/colour pairs) — full sectors in both directions — and
+// each thread has two independent pairs in flight.
+constexpr int kPairsPerThread = 2;
+constexpr int kTile = kThreads * 2 * kPairsPerThread;   // 1024 elements per block step
+
+// streaming (read-once) loads / stores: keep L1/L2 for the gathered vectors
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ double2 ld_stream2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st_stream2(double *p, double a, double b) {
+  __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+}
+
+// two consecutive colour ids with ONE load (16 / 32 / 64 bit)
+template <typename CT> __device__ __forceinline__ void ld_color_pair(const CT *p, uint32_t &a, uint32_t &b);
+template <> __device__ __forceinline__ void ld_color_pair<uint8_t>(const uint8_t *p, uint32_t &a, uint32_t &b) {
+  const uint16_t v = __ldcs(reinterpret_cast<const unsigned short *>(p));
+  a = v & 0xFFu; b = v >> 8;
+}
+template <> __device__ __forceinline__ void ld_color_pair<uint16_t>(const uint16_t *p, uint32_t &a, uint32_t &b) {
+  const uint32_t v = __ldcs(reinterpret_cast<const unsigned int *>(p));
+  a = v & 0xFFFFu; b = v >> 16;
+}
+template <> __device__ __forceinline__ void ld_color_pair<int32_t>(const int32_t *p, uint32_t &a, uint32_t &b) {
+  const int2 v = __ldcs(reinterpret_cast<const int2 *>(p));
+  a = (uint32_t)v.x; b = (uint32_t)v.y;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -88,6 +89,8 @@ struct fdb_plan {
   double *eps = nullptr, *sumsq = nullptr, *partial = nullptr;
   int eps_blocks = 0;
   int64_t eps_chunk = 0;
+  unsigned int *ticket = nullptr;   // last-block-done counter of color_sumsq_reg
+  bool peers_aligned = true;
   // scratch
   double *fx_own = nullptr, *Fp = nullptr, *Fm = nullptr, *xp = nullptr, *xm = nullptr;
   int64_t slabs = 0, ldF = 0, ldx = 0, batch = 1, n_groups = 0;
@@ -254,12 +257,15 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   TRY(P->alloc_t(&P->sumsq, std::max<int32_t>(C, 1)));
   {
     int64_t nb = (P->n + 2047) / 2048;
-    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * 8));
+    // window path: 32 KB of shared memory per block -> keep the grid within one resident wave
+    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * (C <= kEpsRegColors ? 8 : 4)));
     P->eps_blocks = (int)nb;
     int64_t chunk = (P->n + nb - 1) / nb;
     P->eps_chunk = std::max<int64_t>(chunk, 1);
     const int64_t stride = C <= kEpsRegColors ? kEpsRegColors : std::min<int64_t>(C, kEpsWindow);
     TRY(P->alloc_t(&P->partial, (size_t)nb * stride));
+    TRY(P->alloc_t(&P->ticket, 4));
+    CU(cudaMemset(P->ticket, 0, 16));
   }
 
   // scratch: stacked f! outputs (slabs) + perturbed points
@@ -690,6 +696,9 @@ fdb_status fdb_plan_set_peers(fdb_plan *P, int n_peers, double *const *peer_J) {
   if (!P->d_peers) TRY(P->alloc_t(&P->d_peers, 64));
   if (n_peers > 0) CU(cudaMemcpy(P->d_peers, peer_J, (size_t)n_peers * sizeof(double *), cudaMemcpyHostToDevice));
   P->n_peers = n_peers;
+  P->peers_aligned = true;
+  for (int i = 0; i < n_peers; ++i)
+    if (reinterpret_cast<uintptr_t>(peer_J[i]) & 15) P->peers_aligned = false;
   return FDB_OK;
 }
 
@@ -721,26 +730,48 @@ static fdb_status call_f(fdb_plan *P, fdb_fn f, void *ctx, double *fx, const dou
   return FDB_OK;
 }
 
+// Persistent-grid sizing: exactly the number of blocks that are resident at once (SMs x blocks/SM from the occupancy
+// calculator), capped by the work — a single full wave, no partial-wave tail (the r1 ncu capture showed 1184 blocks on
+// 888 resident slots costing a half-empty second wave).
+template <typename K>
+static int resident_grid(const fdb_plan *P, K kernel, size_t dyn_smem, int64_t work_blocks) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  int64_t g = (int64_t)P->sm_count * per_sm;
+  if (g > work_blocks) g = work_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 template <typename CT>
 static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double absstep, double dir, cudaStream_t s) {
   const int32_t C = P->C;
   if (C <= 0) return FDB_OK;
-  const int central = P->fdtype == FDB_CENTRAL;
+  EpsParams prm{P->fdtype == FDB_CENTRAL ? 1 : 0, relstep, absstep, dir};
   if (C <= kEpsRegColors) {
-    color_sumsq_reg<CT><<<P->eps_blocks, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, P->eps_chunk, P->partial);
-    finalize_eps<<<(C * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, kEpsRegColors, 0, C,
-                                                                      central, relstep, absstep, dir, P->eps, P->sumsq);
-    P->cnt.kernel_launches += 2;
+    const int64_t ntiles = (P->n + kTile - 1) / kTile;
+    const int aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (C <= 4) {
+      int grid = std::min(resident_grid(P, color_sumsq_reg<CT, 4>, 0, ntiles), P->eps_blocks);  // partial capacity
+      color_sumsq_reg<CT, 4><<<grid, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, aligned, C, prm, P->partial,
+                                                        P->ticket, P->eps, P->sumsq);
+    } else {
+      int grid = std::min(resident_grid(P, color_sumsq_reg<CT, 8>, 0, ntiles), P->eps_blocks);
+      color_sumsq_reg<CT, 8><<<grid, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, aligned, C, prm, P->partial,
+                                                        P->ticket, P->eps, P->sumsq);
+    }
+    P->cnt.kernel_launches += 1;
   } else {
     for (int32_t k0 = 0; k0 < C; k0 += kEpsWindow) {
       const int32_t W = std::min<int32_t>(kEpsWindow, C - k0);
-      const int32_t stride = std::min<int32_t>(C, kEpsWindow);
       color_sumsq_win<CT><<<P->eps_blocks, kThreads, (size_t)kEpsWarps * W * sizeof(double), s>>>(
           x, (const CT *)P->jcolor, P->n, P->eps_chunk, k0, W, P->partial);
       // partial rows are W wide for this pass
-      finalize_eps<<<(W * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, W, k0, W, central,
-                                                                        relstep, absstep, dir, P->eps, P->sumsq);
-      (void)stride;
+      finalize_eps<<<(W * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, W, k0, W, prm,
+                                                                        P->eps, P->sumsq);
       P->cnt.kernel_launches += 2;
     }
   }
@@ -771,10 +802,23 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     const int64_t G = std::min<int64_t>(P->slabs, n_local - l0);
     for (int64_t b0 = 0; b0 < G; b0 += P->batch) {
       const int64_t kc = std::min<int64_t>(P->batch, G - b0);
-      perturb_colors<CT, CENTRAL><<<P->grid(P->n), kThreads, 0, s>>>(
-          x, (const CT *)P->jcolor, P->eps, P->d_local_colors + l0 + b0, (int32_t)kc, P->C, P->no_drift ? 0 : 1, P->n,
-          P->ldx, P->xp, P->xm);
-      P->cnt.kernel_launches += 1;
+      for (int64_t q0 = 0; q0 < kc; q0 += kPerturbMaxPoints) {
+        PerturbArgs pa{};
+        pa.x = x; pa.jcolor = P->jcolor; pa.eps = P->eps;
+        pa.xp = P->xp + q0 * P->ldx; pa.xm = CENTRAL ? P->xm + q0 * P->ldx : nullptr;
+        pa.n = P->n; pa.ldx = P->ldx; pa.C = P->C; pa.drift = P->no_drift ? 0 : 1;
+        pa.kcount = (int32_t)std::min<int64_t>(kPerturbMaxPoints, kc - q0);
+        for (int32_t q = 0; q < pa.kcount; ++q) pa.k[q] = P->local_colors[(size_t)(l0 + b0 + q0 + q)];
+        pa.aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(P->xp) |
+                       reinterpret_cast<uintptr_t>(P->xm)) & 15) == 0 && (P->ldx & 1) == 0;
+        const size_t sm = P->C <= kPerturbSmemColors ? (size_t)P->C * sizeof(double) : 0;
+        const int64_t tiles = (P->n + kTile - 1) / kTile;
+        if (pa.kcount == 1)
+          perturb_colors<CT, CENTRAL, 1><<<resident_grid(P, perturb_colors<CT, CENTRAL, 1>, sm, tiles), kThreads, sm, s>>>(pa);
+        else
+          perturb_colors<CT, CENTRAL, kPerturbMaxPoints><<<resident_grid(P, perturb_colors<CT, CENTRAL, kPerturbMaxPoints>, sm, tiles), kThreads, sm, s>>>(pa);
+        P->cnt.kernel_launches += 1;
+      }
       TRY(call_f(P, f, ctx, P->Fp + b0 * P->ldF, P->xp, kc, s));               // f(fx1, x1)  :563 / :605
       if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + b0 * P->ldF, P->xm, kc, s));   // f(fx, x)    :606
     }
@@ -803,9 +847,24 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.l0 = (int32_t)l0; a.G = (int32_t)G;
       a.write_invalid_zero = (g == 0 && P->rank == 0 && P->has_invalid) ? 1 : 0;
       a.ldF = P->ldF; a.E = P->E;
+      a.j_aligned = (reinterpret_cast<uintptr_t>(J) & 15) == 0 && P->peers_aligned;
+      const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
       ScatterTimer tm(P, s);
-      if (ident) diff_scatter_ident<CT, CENTRAL><<<P->grid((P->E + kScatterVec - 1) / kScatterVec + 1), kThreads, 0, s>>>(a);
-      else diff_scatter_dest<CT, CENTRAL><<<P->grid(P->E), kThreads, 0, s>>>(a);
+      if (ident) {
+        const int64_t tiles = (P->E + kTile - 1) / kTile;
+        // single group on a single rank: every valid colour is resident -> the FULL variant (no ownership tests)
+        const bool full = P->n_groups == 1 && P->world == 1 && P->n_peers == 0;
+        if (full) {
+          const int grid = resident_grid(P, diff_scatter_ident<CT, CENTRAL, true, kScatterMinBlocks>, sm, tiles);
+          diff_scatter_ident<CT, CENTRAL, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
+        } else {
+          const int grid = resident_grid(P, diff_scatter_ident<CT, CENTRAL, false, kScatterMinBlocks>, sm, tiles);
+          diff_scatter_ident<CT, CENTRAL, false, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
+        }
+      } else {
+        const int grid = resident_grid(P, diff_scatter_dest<CT, CENTRAL>, sm, (P->E + kThreads - 1) / kThreads);
+        diff_scatter_dest<CT, CENTRAL><<<grid, kThreads, sm, s>>>(a);
+      }
       P->cnt.kernel_launches += 1;
       P->cnt.scatter_launches += 1;
     }

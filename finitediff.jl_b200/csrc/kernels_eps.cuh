@@ -16,38 +16,107 @@ constexpr int kEpsRegColors = 8;     // register path when C <= 8
 constexpr int kEpsWindow = 512;      // colours per pass on the shared-memory path
 constexpr int kEpsWarps = kThreads / 32;
 
-// C <= 8: per-thread register accumulators, shuffle tree, fixed warp order.
-template <typename CT>
+struct EpsParams {
+  int fdtype_central;
+  double relstep, absstep, dir;
+};
+
+// the step-size formula from a colour's sum of squares
+__device__ __forceinline__ double eps_from_sumsq(double ss, const EpsParams &p) {
+  const double tmp = sqrt(ss);                        // norm(x2)                     jacobians.jl:560
+  const double a = p.relstep * fabs(sqrt(tmp));       // relstep*abs(sqrt(tmp))       :561 + epsilons.jl:28
+  double e = a > p.absstep ? a : p.absstep;           // max(.., absstep)
+  if (!p.fdtype_central) e = e * p.dir;               // *dir (forward only)          epsilons.jl:28 vs :52
+  return e;
+}
+
+// C <= 8: per-thread register accumulators (NC = 4 or 8 of them) over the block's tiles (fixed tile -> block -> lane
+// mapping), shuffle tree, fixed warp order; the LAST block to finish (atomic ticket) reduces the block partials in
+// fixed order and applies the step-size formula — one launch, no host involvement, bit-reproducible for a given grid.
+template <int NC>
+__device__ __forceinline__ void sumsq_accumulate(double (&acc)[NC], double v, uint32_t c) {
+  const double sq = v * v;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) acc[k] += (c == (uint32_t)k) ? sq : 0.0;
+}
+
+template <typename CT, int NC>
 __global__ void __launch_bounds__(kThreads)
-color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int64_t chunk,
-                double *__restrict__ partial /* [gridDim.x][kEpsRegColors] */) {
-  const int64_t start = (int64_t)blockIdx.x * chunk;
-  int64_t end = start + chunk;
-  if (end > n) end = n;
-  double acc[kEpsRegColors];
+color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int x_aligned, int32_t C,
+                EpsParams prm, double *__restrict__ partial /* [gridDim.x][kEpsRegColors] */,
+                unsigned int *__restrict__ ticket, double *__restrict__ eps, double *__restrict__ sumsq) {
+  double acc[NC];
 #pragma unroll
-  for (int k = 0; k < kEpsRegColors; ++k) acc[k] = 0.0;
-  for (int64_t j = start + threadIdx.x; j < end; j += kThreads) {
-    const double v = x[j];
-    const uint32_t c = (uint32_t)jcolor[j];
-    const double sq = v * v;
+  for (int k = 0; k < NC; ++k) acc[k] = 0.0;
+  constexpr int kHalf = kTile / 2;
+  const int64_t nfull = x_aligned ? n / kTile : 0;
+  const int tid2 = 2 * threadIdx.x;
+  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
+    const double *__restrict__ xt = x + tile * kTile;
+    const CT *__restrict__ ct = jcolor + tile * kTile;
+    const double2 va = ld_stream2(xt + tid2);
+    const double2 vb = ld_stream2(xt + kHalf + tid2);
+    uint32_t ca0, ca1, cb0, cb1;
+    ld_color_pair<CT>(ct + tid2, ca0, ca1);
+    ld_color_pair<CT>(ct + kHalf + tid2, cb0, cb1);
+    sumsq_accumulate<NC>(acc, va.x, ca0);
+    sumsq_accumulate<NC>(acc, va.y, ca1);
+    sumsq_accumulate<NC>(acc, vb.x, cb0);
+    sumsq_accumulate<NC>(acc, vb.y, cb1);
+  }
+  // remainder (or everything, when x is not 16-byte aligned): scalar, same lane order
+  {
+    const int64_t rem0 = nfull * kTile;
+    const int64_t ntail = (n - rem0 + kTile - 1) / kTile;
+    for (int64_t tt = blockIdx.x; tt < ntail; tt += gridDim.x) {
+      const int64_t base = rem0 + tt * kTile;
 #pragma unroll
-    for (int k = 0; k < kEpsRegColors; ++k) acc[k] += (c == (uint32_t)k) ? sq : 0.0;
+      for (int u = 0; u < kPairsPerThread; ++u) {
+        const int64_t j = base + u * kHalf + tid2;
+        if (j < n) sumsq_accumulate<NC>(acc, ld_stream(x + j), (uint32_t)jcolor[j]);
+        if (j + 1 < n) sumsq_accumulate<NC>(acc, ld_stream(x + j + 1), (uint32_t)jcolor[j + 1]);
+      }
+    }
   }
   __shared__ double s[kEpsWarps][kEpsRegColors];
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < kEpsRegColors; ++k) {
+  for (int k = 0; k < NC; ++k) {
     const double t = warp_sum(acc[k]);
     if (lane == 0) s[w][k] = t;
   }
   __syncthreads();
-  if (threadIdx.x < kEpsRegColors) {
+  if (threadIdx.x < NC) {
     double t = 0.0;
 #pragma unroll
     for (int ww = 0; ww < kEpsWarps; ++ww) t += s[ww][threadIdx.x];
-    partial[(int64_t)blockIdx.x * kEpsRegColors + threadIdx.x] = t;
+    __stcg(partial + (int64_t)blockIdx.x * kEpsRegColors + threadIdx.x, t);
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // last block: warp w reduces colour w over the blocks (lanes stride the blocks, then a shuffle tree)
+  static_assert(kEpsWarps == kEpsRegColors, "one warp per register colour");
+  if (w < C) {
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;   // 4 independent chains (fixed order): loads overlap
+    int b = lane;
+    for (; b + 96 < (int)gridDim.x; b += 128) {
+      t0 += __ldcg(partial + (int64_t)b * kEpsRegColors + w);
+      t1 += __ldcg(partial + (int64_t)(b + 32) * kEpsRegColors + w);
+      t2 += __ldcg(partial + (int64_t)(b + 64) * kEpsRegColors + w);
+      t3 += __ldcg(partial + (int64_t)(b + 96) * kEpsRegColors + w);
+    }
+    for (; b < (int)gridDim.x; b += 32) t0 += __ldcg(partial + (int64_t)b * kEpsRegColors + w);
+    double t = warp_sum((t0 + t1) + (t2 + t3));
+    if (lane == 0) {
+      eps[w] = eps_from_sumsq(t, prm);
+      if (sumsq) sumsq[w] = t;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next call (stream-ordered)
 }
 
 // General C: colours [k0, k0+W) per pass; every warp owns a private W-entry accumulator in shared memory, lanes that
@@ -101,8 +170,8 @@ color_sumsq_win(const double *__restrict__ x, const CT *__restrict__ jcolor, int
 // One warp per colour: fixed-order reduction over the block partials, then the step-size formula.
 __global__ void __launch_bounds__(kThreads)
 finalize_eps(const double *__restrict__ partial, int32_t nblocks, int32_t stride /* colours per partial row */,
-             int32_t k0, int32_t ncolors_here, int fdtype_central, double relstep, double absstep, double dir,
-             double *__restrict__ eps /* [C] */, double *__restrict__ sumsq /* [C] or null */) {
+             int32_t k0, int32_t ncolors_here, EpsParams prm, double *__restrict__ eps /* [C] */,
+             double *__restrict__ sumsq /* [C] or null */) {
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5);
   if (c >= ncolors_here) return;
@@ -110,11 +179,7 @@ finalize_eps(const double *__restrict__ partial, int32_t nblocks, int32_t stride
   for (int b = lane; b < nblocks; b += 32) t += partial[(int64_t)b * stride + c];
   t = warp_sum(t);
   if (lane == 0) {
-    const double tmp = sqrt(t);                      // norm(x2)                     jacobians.jl:560
-    const double a = relstep * fabs(sqrt(tmp));      // relstep*abs(sqrt(tmp))       :561 + epsilons.jl:28
-    double e = a > absstep ? a : absstep;            // max(.., absstep)
-    if (!fdtype_central) e = e * dir;                // *dir (forward only)          epsilons.jl:28 vs :52
-    eps[k0 + c] = e;
+    eps[k0 + c] = eps_from_sumsq(t, prm);
     if (sumsq) sumsq[k0 + c] = t;
   }
 }

