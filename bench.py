@@ -161,10 +161,11 @@ def cpu_jacobian_runner(workload, fdtype, nthreads, scale=1.0):
         P = orc.Problem.csc_same(n, n, colptr, rowval)
         x = orc.fill_x(n, SEED + 4, nthreads)
         nz = np.zeros(len(rowval))
-        ctx = orc.SynthEllCtx(n, 8, cols.ctypes.data_as(C.POINTER(C.c_int32)), coef.ctypes.data_as(C.POINTER(C.c_double)), nthreads)
+        colsT, coefT = np.ascontiguousarray(cols.T), np.ascontiguousarray(coef.T)     # ELL layout [K][m]
+        ctx = orc.SynthEllCtx(n, 8, colsT.ctypes.data_as(C.POINTER(C.c_int32)), coefT.ctypes.data_as(C.POINTER(C.c_double)), nthreads)
         cache = dict(x1=np.zeros(n), x2=np.zeros(n), fx=np.zeros(n), fx1=np.zeros(n))
         fn = orc.native_fn("synth_ellrows")
-        keep = (cols, coef)
+        keep = (colsT, coefT)
 
         def run(_keep=keep):
             return orc.jacobian(P, nz, fn, x, fdtype=fd, colorvec=cv, nthreads=nthreads, ctx=ctx, cache=cache)["fcalls"]
@@ -249,14 +250,26 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
         return dict(J=J, f=f, x=x, cache=cache, nnz=3 * n - 2, n=n, ctx=ctx, keep=(colptr, rowval, cv))
     if workload == "c4":
         n, K, Cc = 5_000_000, 8, 64
-        cols, coef = ell_problem(n, K, Cc, 11)
-        colptr, rowval = ell_csc(n, K, cols)
+        # generated on the device (same seed on every rank -> identical problem): row i takes K distinct colours
+        # (base + j*odd_stride mod 64) and one random column of each; ELL layout [K][n]; CSC = its transpose
+        g = torch.Generator(device=dev).manual_seed(11)
+        base = torch.randint(0, Cc, (n,), device=dev, generator=g, dtype=torch.int64)
+        stride = torch.randint(0, Cc // 2, (n,), device=dev, generator=g, dtype=torch.int64) * 2 + 1
+        colors = (base[None, :] + torch.arange(K, device=dev)[:, None] * stride[None, :]) % Cc
+        which = torch.randint(0, n // Cc, (K, n), device=dev, generator=g, dtype=torch.int64)
+        cols64 = which * Cc + colors
+        d_cols = cols64.to(torch.int32).contiguous()
+        d_coef = torch.rand((K, n), device=dev, generator=g, dtype=torch.float64) * 2 - 1
+        rows = torch.arange(n, device=dev, dtype=torch.int64).repeat(K)
+        order = torch.argsort(cols64.reshape(-1) * n + rows)
+        rowval = (rows[order] + 1).contiguous()
+        colptr = torch.cat([torch.ones(1, dtype=torch.int64, device=dev),
+                            1 + torch.cumsum(torch.bincount(cols64.reshape(-1), minlength=n), 0)])
+        del colors, which, cols64, rows, order, base, stride
         cv = (torch.arange(n, dtype=torch.int64, device=dev) % Cc) + 1
         x = torch.empty(n, dtype=torch.float64, device=dev)
         synth.fdbs_fill_x(x.data_ptr(), n, SEED + 4, None)
-        d_cols = torch.from_numpy(cols).to(dev)
-        d_coef = torch.from_numpy(coef).to(dev)
-        J = pkg.SparseMatrixCSC(n, n, torch.from_numpy(colptr).to(dev), torch.from_numpy(rowval).to(dev),
+        J = pkg.SparseMatrixCSC(n, n, colptr, rowval,
                                 torch.full((n * K,), float("nan"), dtype=torch.float64, device=dev))
         ctx = L.EllCtx(n, K, d_cols.data_ptr(), d_coef.data_ptr(), 0)
         f = native("fdbs_ellrows", ctx, max_batch)

@@ -25,7 +25,7 @@ class PlanOpts(C.Structure):
     _fields_ = [
         ("fdtype", C.c_int32), ("device", C.c_int32), ("use_current_device", C.c_int32), ("no_drift", C.c_int32),
         ("max_batch", C.c_int64), ("scratch_bytes", C.c_int64),
-        ("rank", C.c_int32), ("world", C.c_int32), ("partition", C.c_int32), ("reserved", C.c_int32),
+        ("rank", C.c_int32), ("world", C.c_int32), ("partition", C.c_int32), ("strategy", C.c_int32),
     ]
 
 
@@ -35,7 +35,7 @@ class PlanInfo(C.Structure):
         ("n_colors", C.c_int64), ("n_local_colors", C.c_int64), ("n_groups", C.c_int64), ("slabs", C.c_int64),
         ("fcalls_per_jacobian", C.c_int64), ("device_bytes", C.c_int64),
         ("fdtype", C.c_int32), ("jkind", C.c_int32), ("sp_kind", C.c_int32), ("color_bits", C.c_int32),
-        ("alg_bytes_scatter", C.c_int64),
+        ("alg_bytes_scatter", C.c_int64), ("strategy", C.c_int32), ("lanes", C.c_int32), ("mean_row_jump", C.c_double),
     ]
 
     def as_dict(self):

@@ -14,6 +14,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -94,6 +95,15 @@ struct fdb_plan {
   // scratch
   double *fx_own = nullptr, *Fp = nullptr, *Fm = nullptr, *xp = nullptr, *xm = nullptr;
   int64_t slabs = 0, ldF = 0, ldx = 0, batch = 1, n_groups = 0;
+  int64_t pbatch = 1;   // perturbed points built per perturb pass (>= batch): x is read once for all of them
+  // scatter strategy (CSC plans): 0 = one fused pass over J's storage order (row-local patterns), 1 = per-colour
+  // column lists launched right after the colour's f! (random patterns: the slab is gathered from L2; multi-GPU)
+  int strategy = 0;
+  bool strategy_auto = true;
+  int32_t *colptr32 = nullptr, *cols_by_color = nullptr;
+  std::vector<int64_t> bucket_start;   // [C+2] offsets into cols_by_color; bucket C = columns without a valid colour
+  int lanes = 1;
+  double mean_row_jump = 0.0;
   // peers (multi-GPU fused gather)
   double **d_peers = nullptr;
   int n_peers = 0;
@@ -278,17 +288,28 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   const int64_t per_slab = 8 * P->ldF * (central ? 2 : 1);
   int64_t slabs = std::max<int64_t>(1, budget / per_slab);
   slabs = std::min<int64_t>(slabs, std::max<int64_t>(n_local, 1));
+  if (P->sp_kind == SP_CSC && P->strategy == 0 && P->strategy_auto && slabs < n_local) P->strategy = 1;
+  if (P->strategy == 1) {
+    // per-colour lists: keep only as many f! outputs in flight as stay L2-resident until their scatter (~48 MB)
+    const int64_t l2_slabs = std::max<int64_t>(1, (int64_t)48000000 / per_slab);
+    slabs = std::min<int64_t>(slabs, l2_slabs);
+  }
   P->slabs = slabs;
   P->n_groups = n_local == 0 ? 0 : (n_local + slabs - 1) / slabs;
   int64_t batch = (o && o->max_batch > 1) ? o->max_batch : 1;
   batch = std::min<int64_t>(batch, slabs);
   P->batch = batch;
+  // even when f! takes one point per call, build up to kPerturbMaxPoints points per pass over x (one read of x and
+  // the colour stream instead of one per colour) when the point buffers fit in an eighth of the scratch budget
+  int64_t pbatch = std::max<int64_t>(batch, std::min<int64_t>(kPerturbMaxPoints, std::max<int64_t>(n_local, 1)));
+  while (pbatch > batch && pbatch * 8 * P->ldx * (central ? 2 : 1) > budget / 8) --pbatch;
+  P->pbatch = pbatch;
   TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
   TRY(P->alloc_t(&P->Fp, (size_t)slabs * P->ldF));
-  TRY(P->alloc_t(&P->xp, (size_t)batch * P->ldx));
+  TRY(P->alloc_t(&P->xp, (size_t)pbatch * P->ldx));
   if (central) {
     TRY(P->alloc_t(&P->Fm, (size_t)slabs * P->ldF));
-    TRY(P->alloc_t(&P->xm, (size_t)batch * P->ldx));
+    TRY(P->alloc_t(&P->xm, (size_t)pbatch * P->ldx));
   }
   return FDB_OK;
 }
@@ -460,6 +481,61 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     cudaError_t e = cudaMemcpy(cnt.data(), d_cnt, (size_t)P->C * 8, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "colour counts: %s", cudaGetErrorString(e)); }
   }
+  // ---- per-colour column lists + gather-locality metric -> scatter strategy
+  {
+    const int32_t C = P->C;
+    unsigned long long *d_bucket = nullptr, *d_jump = nullptr;
+    PLAN_TRY(P->alloc_t(&d_bucket, (size_t)C + 2));
+    PLAN_TRY(P->alloc_t(&d_jump, 1));
+    cudaMemset(d_bucket, 0, ((size_t)C + 2) * 8);
+    cudaMemset(d_jump, 0, 8);
+    PLAN_TRY(P->alloc_t(&P->colptr32, (size_t)n + 1));
+    PLAN_TRY(P->alloc_t(&P->cols_by_color, (size_t)std::max<int64_t>(n, 1)));
+    PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      colptr32_and_count<CT><<<P->grid(n + 1), kThreads>>>(cp.d, n, (const CT *)P->jcolor, C, P->colptr32, d_bucket);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+    std::vector<unsigned long long> bc((size_t)C + 1, 0);
+    {
+      cudaError_t e = cudaMemcpy(bc.data(), d_bucket, ((size_t)C + 1) * 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "column buckets: %s", cudaGetErrorString(e)); }
+    }
+    P->bucket_start.assign((size_t)C + 2, 0);
+    for (int32_t k = 0; k <= C; ++k) P->bucket_start[(size_t)k + 1] = P->bucket_start[(size_t)k] + (int64_t)bc[(size_t)k];
+    std::vector<unsigned long long> cursor(P->bucket_start.begin(), P->bucket_start.begin() + C + 1);
+    cudaMemcpy(d_bucket, cursor.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice);
+    if (n > 0) {
+      PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+        using CT = decltype(tag);
+        bucket_columns<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, n, C, d_bucket, P->cols_by_color);
+        CU(cudaGetLastError());
+        return FDB_OK;
+      }));
+    }
+    if (nnz > 1) {
+      row_jump_sum<<<P->grid(nnz), kThreads>>>(P->row32, nnz, d_jump);
+      unsigned long long js = 0;
+      cudaMemcpy(&js, d_jump, 8, cudaMemcpyDeviceToHost);
+      P->mean_row_jump = (double)js / (double)(nnz - 1);
+    }
+    int lanes = 1;
+    const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
+    while (lanes < 32 && lanes < avg) lanes *= 2;
+    P->lanes = lanes;
+    // strategy: opts->strategy 1 = fused, 2 = per-colour lists, 0 = auto.  Measured on B200 (profiles/r1): on ONE GPU
+    // the fused pass wins even for random patterns (C4: 1.39 ms vs 64 x 29 us) — every 64-byte line of a slab is
+    // fetched once either way and the fused launch keeps f(x) L2-resident; the lists win whenever a launch would
+    // otherwise stream entries it does not own: several ranks sharing the colours, or more colours than resident
+    // slabs (decided in finish_colored_plan).
+    const int want = opts ? opts->strategy : 0;
+    bool per_color = P->world > 1;
+    if (want == 1) per_color = false;
+    if (want == 2) per_color = true;
+    P->strategy = per_color ? 1 : 0;
+    P->strategy_auto = want == 0;
+  }
   PLAN_TRY(finish_colored_plan(P, opts, cnt));
   // B_alg = 32*nnz + 16*n + 8 (valid colouring; Int64 indices as at the ABI)
   P->alg_bytes = 32 * nnz + 16 * n + 8;
@@ -625,6 +701,9 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
   info->sp_kind = P->sp_kind;
   info->color_bits = P->color_bits;
   info->alg_bytes_scatter = P->alg_bytes;
+  info->strategy = P->strategy;
+  info->lanes = P->lanes;
+  info->mean_row_jump = P->mean_row_jump;
   return FDB_OK;
 }
 
@@ -797,18 +876,15 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     if (f_in) vfx = f_in;                                  // jacobians.jl:543-544
     else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; } // :541-542
   }
-  for (int64_t g = 0; g < P->n_groups; ++g) {
-    const int64_t l0 = g * P->slabs;
-    const int64_t G = std::min<int64_t>(P->slabs, n_local - l0);
-    for (int64_t b0 = 0; b0 < G; b0 += P->batch) {
-      const int64_t kc = std::min<int64_t>(P->batch, G - b0);
+  // build the perturbed points of local colours [li0, li0+kc) into the point buffers (one pass over x per 4 colours)
+  auto perturb_window = [&](int64_t li0, int64_t kc) -> fdb_status {
       for (int64_t q0 = 0; q0 < kc; q0 += kPerturbMaxPoints) {
         PerturbArgs pa{};
         pa.x = x; pa.jcolor = P->jcolor; pa.eps = P->eps;
         pa.xp = P->xp + q0 * P->ldx; pa.xm = CENTRAL ? P->xm + q0 * P->ldx : nullptr;
         pa.n = P->n; pa.ldx = P->ldx; pa.C = P->C; pa.drift = P->no_drift ? 0 : 1;
         pa.kcount = (int32_t)std::min<int64_t>(kPerturbMaxPoints, kc - q0);
-        for (int32_t q = 0; q < pa.kcount; ++q) pa.k[q] = P->local_colors[(size_t)(l0 + b0 + q0 + q)];
+        for (int32_t q = 0; q < pa.kcount; ++q) pa.k[q] = P->local_colors[(size_t)(li0 + q0 + q)];
         pa.aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(P->xp) |
                        reinterpret_cast<uintptr_t>(P->xm)) & 15) == 0 && (P->ldx & 1) == 0;
         const size_t sm = P->C <= kPerturbSmemColors ? (size_t)P->C * sizeof(double) : 0;
@@ -819,9 +895,61 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
           perturb_colors<CT, CENTRAL, kPerturbMaxPoints><<<resident_grid(P, perturb_colors<CT, CENTRAL, kPerturbMaxPoints>, sm, tiles), kThreads, sm, s>>>(pa);
         P->cnt.kernel_launches += 1;
       }
-      TRY(call_f(P, f, ctx, P->Fp + b0 * P->ldF, P->xp, kc, s));               // f(fx1, x1)  :563 / :605
-      if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + b0 * P->ldF, P->xm, kc, s));   // f(fx, x)    :606
+      return FDB_OK;
+  };
+
+  // per-colour column-list scatter of local colours [l0, l0+G): <= kMaxSegs colours per launch
+  auto scatter_lists = [&](int64_t g, int64_t l0, int64_t G) -> fdb_status {
+    const bool zero_bucket = g == 0 && P->rank == 0 && P->bucket_start[(size_t)P->C + 1] > P->bucket_start[(size_t)P->C];
+    int64_t li = l0;
+    bool zero_done = !zero_bucket;
+    while (li < l0 + G || !zero_done) {
+      ColScatterArgs a{};
+      a.cols = P->cols_by_color; a.colptr32 = P->colptr32; a.row = P->row32; a.dest = P->dest;
+      a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
+      a.ldF = P->ldF;
+      int ns = 0;
+      a.seg_cum[0] = 0;
+      if (!zero_done) {
+        a.seg_start[ns] = P->bucket_start[(size_t)P->C];
+        a.seg_color[ns] = -1; a.seg_slab[ns] = 0;
+        a.seg_cum[ns + 1] = a.seg_cum[ns] + (P->bucket_start[(size_t)P->C + 1] - P->bucket_start[(size_t)P->C]);
+        ++ns;
+        zero_done = true;
+      }
+      for (; li < l0 + G && ns < kMaxSegs; ++li) {
+        const int32_t k = P->local_colors[(size_t)li];
+        a.seg_start[ns] = P->bucket_start[(size_t)k];
+        a.seg_color[ns] = k; a.seg_slab[ns] = (int32_t)(li - l0);
+        a.seg_cum[ns + 1] = a.seg_cum[ns] + (P->bucket_start[(size_t)k + 1] - P->bucket_start[(size_t)k]);
+        ++ns;
+      }
+      a.n_segs = ns;
+      const int64_t total = a.seg_cum[ns];
+      if (total == 0) continue;
+      ScatterTimer tm(P, s);
+      auto go = [&](auto lanes_tag) {
+        constexpr int LANES = decltype(lanes_tag)::value;
+        const int64_t blocks = (total + (kThreads / LANES) - 1) / (kThreads / LANES);
+        const int grid = resident_grid(P, diff_scatter_cols<CENTRAL, LANES>, 0, blocks);
+        diff_scatter_cols<CENTRAL, LANES><<<grid, kThreads, 0, s>>>(a);
+      };
+      switch (P->lanes) {
+        case 1: go(std::integral_constant<int, 1>{}); break;
+        case 2: go(std::integral_constant<int, 2>{}); break;
+        case 4: go(std::integral_constant<int, 4>{}); break;
+        case 8: go(std::integral_constant<int, 8>{}); break;
+        case 16: go(std::integral_constant<int, 16>{}); break;
+        default: go(std::integral_constant<int, 32>{}); break;
+      }
+      P->cnt.kernel_launches += 1;
+      P->cnt.scatter_launches += 1;
     }
+    return FDB_OK;
+  };
+
+  auto scatter_group = [&](int64_t g, int64_t l0, int64_t G) -> fdb_status {
+    if (P->sp_kind == SP_CSC && P->strategy == 1) return scatter_lists(g, l0, G);
     if (P->sp_kind == SP_BANDED) {
       BandArgs a{};
       a.jcolor = P->jcolor; a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps; a.local_of = P->local_of;
@@ -868,7 +996,25 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       P->cnt.kernel_launches += 1;
       P->cnt.scatter_launches += 1;
     }
+    return FDB_OK;
+  };
+
+  // colours ascending (jacobians.jl:547).  Points are built in windows of `pbatch` colours, f! is called once per point
+  // (reference order f(fx1,x1) then f(fx,x) per colour, :563 / :605-606) or once per `batch` points for batch-capable
+  // callbacks; a group's scatter is launched as soon as its `slabs` outputs are complete.
+  int64_t li = 0;
+  while (li < n_local) {
+    const int64_t g = li / P->slabs, g0 = g * P->slabs, gend = std::min<int64_t>(g0 + P->slabs, n_local);
+    if (li % P->pbatch == 0) TRY(perturb_window(li, std::min<int64_t>(P->pbatch, n_local - li)));
+    const int64_t wend = std::min<int64_t>((li / P->pbatch + 1) * P->pbatch, n_local);
+    const int64_t fc = std::min<int64_t>(P->batch, std::min<int64_t>(wend - li, gend - li));
+    TRY(call_f(P, f, ctx, P->Fp + (li - g0) * P->ldF, P->xp + (li % P->pbatch) * P->ldx, fc, s));
+    if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + (li - g0) * P->ldF, P->xm + (li % P->pbatch) * P->ldx, fc, s));
+    li += fc;
+    if (li == gend) TRY(scatter_group(g, g0, gend - g0));
   }
+  // columns without a valid colour when this rank evaluates no colour at all
+  if (n_local == 0 && P->sp_kind == SP_CSC && P->strategy == 1 && P->n_peers > 0) TRY(scatter_group(0, 0, 0));
   CU(cudaGetLastError());
   return FDB_OK;
 }

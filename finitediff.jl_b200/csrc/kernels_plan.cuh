@@ -161,6 +161,69 @@ prepare_coo(const int64_t *__restrict__ rows, const int64_t *__restrict__ cols, 
   }
 }
 
+// ---- per-colour column lists (the reference's "for col in 1:ncols; if colorvec[col]==color_i" test, done ONCE) ----
+// colptr32[c] = colptr[c]-1 (0-based int32), column counts per colour bucket (bucket C = columns without a valid colour)
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+colptr32_and_count(const int64_t *__restrict__ colptr, int64_t n, const CT *__restrict__ jcolor, int32_t C,
+                   int32_t *__restrict__ colptr32, unsigned long long *__restrict__ bucket_count /* [C+1] */) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = blockIdx.x * (int64_t)kThreads + threadIdx.x; c <= n; c += stride) {
+    colptr32[c] = (int32_t)(colptr[c] - 1);
+    if (c < n) {
+      uint32_t k = (uint32_t)jcolor[c];
+      if (k >= (uint32_t)C) k = (uint32_t)C;
+      // warp-aggregated histogram: lanes holding the same colour elect a leader that adds the group's population
+      const unsigned act = __activemask();
+      const unsigned peers = __match_any_sync(act, k);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(bucket_count + k, (unsigned long long)__popc(peers));
+    }
+  }
+}
+
+// Warp-ballot compaction of the columns into per-colour lists: every warp takes 32 consecutive columns, lanes with
+// the same colour form a group (match.any), the group's leader reserves `popc` slots in that colour's segment with one
+// atomic, each lane writes at its rank inside the group.  Order inside a segment follows reservation order (close to
+// ascending; the result does not depend on it — every slot of J is written exactly once).
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+bucket_columns(const CT *__restrict__ jcolor, int64_t n, int32_t C, unsigned long long *__restrict__ cursor /* [C+1], starts */,
+               int32_t *__restrict__ cols_by_color) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int lane = threadIdx.x & 31;
+  for (int64_t c0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) - lane; c0 < n; c0 += stride) {
+    const int64_t c = c0 + lane;
+    const bool in = c < n;
+    uint32_t k = in ? (uint32_t)jcolor[c] : 0xFFFFFFFEu;
+    if (in && k >= (uint32_t)C) k = (uint32_t)C;
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const unsigned peers = __match_any_sync(act, k);
+      const int leader = __ffs(peers) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor + k, (unsigned long long)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      cols_by_color[base + rank] = (int32_t)c;
+    }
+  }
+}
+
+// gather-locality metric: sum over entries of min(|row[e+1]-row[e]|, 2^20) (decides fused single pass vs per-colour passes)
+__global__ void __launch_bounds__(kThreads)
+row_jump_sum(const int32_t *__restrict__ row32, int64_t E, unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e + 1 < E; e += stride) {
+    long long d = (long long)row32[e + 1] - row32[e];
+    if (d < 0) d = -d;
+    acc += (unsigned long long)(d > (1 << 20) ? (1 << 20) : d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // per-colour column counts (banded plans: entries per colour = sum of band lengths of its columns)
 template <typename CT>
 __global__ void __launch_bounds__(kThreads)

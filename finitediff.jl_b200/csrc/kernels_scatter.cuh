@@ -198,6 +198,59 @@ diff_scatter_dest(const ScatterArgs a) {
   }
 }
 
+// ---- per-colour column-list scatter (CSC) ----
+// The literal shape of ext/FiniteDiffSparseArraysExt.jl:38-47 — "for every column of colour k, for every stored entry:
+// nzval[p] = vfx[rowval[p]]" — driven by the per-colour column lists built at plan time, LANES lanes per column.
+// Used when the gather pattern is random (no row locality between consecutive entries): launched right after the
+// colour's f! so its output slab F[k] is still L2-resident and the 8-byte random gathers never reach HBM; also the
+// multi-GPU form (a rank touches only the columns of the colours it owns).
+constexpr int kMaxSegs = 8;
+struct ColScatterArgs {
+  const int32_t *cols;       // cols_by_color
+  const int32_t *colptr32;   // [n+1] 0-based
+  const int32_t *row;        // [E]
+  const int64_t *dest;       // [E] or null
+  const double *fx, *Fp, *Fm, *eps;
+  double *J;
+  double *const *peers;
+  int32_t n_peers, n_segs;
+  int64_t ldF;
+  int64_t seg_start[kMaxSegs];   // offset of the segment in cols
+  int64_t seg_cum[kMaxSegs + 1]; // cumulative column counts of the launch's segments
+  int32_t seg_color[kMaxSegs];   // global colour (for eps), or -1: columns without a valid colour -> zeros
+  int32_t seg_slab[kMaxSegs];    // slab index of the colour's f! output
+};
+
+template <bool CENTRAL, int LANES>
+__global__ void __launch_bounds__(kThreads)
+diff_scatter_cols(const ColScatterArgs a) {
+  constexpr int kColsPerBlock = kThreads / LANES;
+  const int sub = threadIdx.x % LANES;
+  const int64_t total = a.seg_cum[a.n_segs];
+  for (int64_t i = blockIdx.x * (int64_t)kColsPerBlock + threadIdx.x / LANES; i < total; i += (int64_t)gridDim.x * kColsPerBlock) {
+    int s = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxSegs; ++q) s += (q < a.n_segs && i >= a.seg_cum[q]) ? 1 : 0;
+    const int32_t c = __ldg(a.cols + a.seg_start[s] + (i - a.seg_cum[s]));
+    const int32_t k = a.seg_color[s];
+    const int32_t p0 = __ldg(a.colptr32 + c), p1 = __ldg(a.colptr32 + c + 1);
+    const double e = k >= 0 ? __ldg(a.eps + k) : 1.0;
+    const double denom = CENTRAL ? 2 * e : e;
+    const double *hi = a.Fp + (int64_t)a.seg_slab[s] * a.ldF;
+    const double *lo = CENTRAL ? a.Fm + (int64_t)a.seg_slab[s] * a.ldF : a.fx;
+    for (int32_t p = p0 + sub; p < p1; p += LANES) {
+      double v = 0.0;
+      if (k >= 0) {
+        const int32_t r = __ldg(a.row + p);
+        v = (__ldg(hi + r) - __ldg(lo + r)) / denom;      // jacobians.jl:565 / :607 fused with ext/..SparseArraysExt.jl:44
+      }
+      const int64_t d = a.dest ? __ldg(a.dest + p) : (int64_t)p;
+      a.J[d] = v;
+      for (int q = 0; q < a.n_peers; ++q) a.peers[q][d] = v;
+    }
+  }
+}
+
 // ---- banded: ext/FiniteDiffBandedMatricesExt.jl:13-27 ----
 // Every in-band (r,c), r in [max(1,c-u), min(m,c+l)], receives vfx[r] of column c's colour: the destination is the
 // contiguous band column data[:,c] (slot u+r-c, 0-based) and the source rows are contiguous too, so this is a

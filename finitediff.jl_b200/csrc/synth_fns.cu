@@ -54,17 +54,16 @@ __global__ void __launch_bounds__(kT) k_lap5(double *__restrict__ out, const dou
   }
 }
 
+// ELL layout [K][m]: entry p of row i at p*m + i -> the index / coefficient streams are read fully coalesced
 __global__ void __launch_bounds__(kT) k_ellrows(double *__restrict__ fx, const double *__restrict__ x, int64_t m, int K,
                                                 const int32_t *__restrict__ cols, const double *__restrict__ coef,
                                                 int64_t ldfx, int64_t ldx) {
   const double *xb = x + (int64_t)blockIdx.y * ldx;
   double *fb = fx + (int64_t)blockIdx.y * ldfx;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < m; i += (int64_t)gridDim.x * kT) {
-    const int32_t *cc = cols + i * K;
-    const double *aa = coef + i * K;
-    const double x0 = __ldg(xb + cc[0]);
-    double s = mul(aa[0], x0);
-    for (int p = 1; p < K; ++p) s = add(s, mul(aa[p], __ldg(xb + cc[p])));
+    const double x0 = __ldg(xb + __ldcs(cols + i));
+    double s = mul(__ldcs(coef + i), x0);
+    for (int p = 1; p < K; ++p) s = add(s, mul(__ldcs(coef + (int64_t)p * m + i), __ldg(xb + __ldcs(cols + (int64_t)p * m + i))));
     s = add(s, mul(0.1, mul(x0, x0)));
     fb[i] = s;
   }

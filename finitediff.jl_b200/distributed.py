@@ -1,0 +1,188 @@
+"""One process per GPU: the colour set of a Jacobian is partitioned over the ranks.
+
+Colours are independent units given x (each colour = perturb -> f! -> diff -> scatter into a disjoint set of J slots),
+so there is NO collective on the data path until the end, where every rank needs the entries the others computed.
+Two implementations of that final exchange:
+
+  "p2p"  (default on NVLink/NVSwitch)  the diff+scatter kernel itself stores every value it owns into EVERY rank's
+         nzval buffer (peer pointers from CUDA IPC, passed to the plan with fdb_plan_set_peers) — compute and gather
+         are one kernel; a stream-ordered NCCL all-reduce of one flag word is the only barrier.
+  "nccl" (fallback; also what the CPU/gloo tests exercise)  each rank packs the entries it owns into a compact
+         buffer, all_gather, then un-permutes into nzval.
+
+torch.distributed is plumbing only (rendezvous, barrier, the fallback all_gather); the hot path is libfdjac_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import api
+
+
+# ------------------------------------------------------------------------------------------------ host-side partition logic
+def partition_colors(n_colors: int, world: int, counts=None, mode: int = 0) -> np.ndarray:
+    """Owner rank of every colour — the same deterministic rule as the plan (csrc/fdjac_abi.cu finish_colored_plan):
+    mode 0 round-robin; mode 1 LPT (heaviest colour first onto the least-loaded rank, ties -> lowest rank)."""
+    owner = np.zeros(n_colors, np.int32)
+    if world <= 1:
+        return owner
+    if mode == 1:
+        counts = np.asarray(counts, dtype=np.uint64)
+        order = sorted(range(n_colors), key=lambda k: -int(counts[k]))   # stable: ties keep ascending colour
+        load = [0] * world
+        for k in order:
+            best = min(range(world), key=lambda r: (load[r], r))
+            owner[k] = best
+            load[best] += int(counts[k]) + 1
+    else:
+        owner[:] = np.arange(n_colors) % world
+    return owner
+
+
+def entry_colors_csc(colptr, colorvec) -> np.ndarray:
+    """0-based colour of every CSC entry (colour of its column); -1 where colorvec < 1."""
+    colptr = np.asarray(colptr, dtype=np.int64)
+    cv = np.asarray(colorvec, dtype=np.int64)
+    per_col = np.diff(colptr)
+    ec = np.repeat(cv - 1, per_col)
+    ec[ec < 0] = -1
+    return ec
+
+
+class GatherPlan:
+    """Index lists for the pack / all_gather / unpack exchange of owned Jacobian entries."""
+
+    def __init__(self, entry_color: np.ndarray, owner: np.ndarray, world: int, device):
+        self.world = world
+        own = np.where(entry_color >= 0, owner[np.clip(entry_color, 0, max(len(owner) - 1, 0))] if len(owner) else 0, 0)
+        self.idx: List[torch.Tensor] = []
+        for r in range(world):
+            self.idx.append(torch.from_numpy(np.nonzero(own == r)[0].astype(np.int64)).to(device))
+        self.pad = max((int(i.numel()) for i in self.idx), default=0)
+
+    def pack(self, values: torch.Tensor, rank: int) -> torch.Tensor:
+        out = torch.zeros(self.pad, dtype=values.dtype, device=values.device)
+        out[: self.idx[rank].numel()] = values.index_select(0, self.idx[rank])
+        return out
+
+    def unpack(self, values: torch.Tensor, gathered: List[torch.Tensor], skip_rank: Optional[int] = None):
+        for r, g in enumerate(gathered):
+            if r == skip_rank:
+                continue
+            values.index_copy_(0, self.idx[r], g[: self.idx[r].numel()])
+
+
+def allgather_owned(values: torch.Tensor, gp: GatherPlan, rank: int, group=None):
+    """values holds this rank's owned entries in place; on return it holds everybody's (gloo or nccl)."""
+    mine = gp.pack(values, rank)
+    gathered = [torch.empty_like(mine) for _ in range(gp.world)]
+    dist.all_gather(gathered, mine, group=group)
+    gp.unpack(values, gathered, skip_rank=rank)
+    return values
+
+
+# ------------------------------------------------------------------------------------------------ device side
+class IpcBuffer:
+    """A float64 device buffer from a dedicated cudaMalloc (so its CUDA IPC handle maps the buffer itself)."""
+
+    def __init__(self, count: int, device: torch.device):
+        self.count = int(count)
+        p = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(L.lib().fdb_device_alloc(C.byref(p), max(self.count, 2) * 8))
+        self.ptr = p.value
+        self.device = device
+        self.tensor = torch.as_tensor(api._DevArray(self.ptr, (self.count,)), device=device)
+
+    def handle(self) -> bytes:
+        h = C.create_string_buffer(64)
+        L.check(L.lib().fdb_ipc_get_handle(C.c_void_p(self.ptr), h))
+        return h.raw
+
+    def free(self):
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                L.lib().fdb_device_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+class ShardedJacobian:
+    """finite_difference_jacobian! with the colours of `cache.colorvec` sharded over the ranks of the default process
+    group (the cache must have been built with rank=, world=).  After run() every rank holds the complete J."""
+
+    def __init__(self, J: api.SparseMatrixCSC, cache: api.JacobianCache, n: int, device, mode: str = "p2p", group=None,
+                 pre_sync: bool = True):
+        if not isinstance(J, api.SparseMatrixCSC):
+            raise TypeError("ShardedJacobian shards CSC Jacobians (dense plans shard columns: Plan.dense_range())")
+        self.J, self.cache, self.n, self.device, self.group = J, cache, n, torch.device(device), group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.pre_sync = pre_sync
+        self.plan = cache.plan_for(J, cache.sparsity, cache.colorvec, n)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.mode = mode
+        self._peers = []
+        self._ipc: Optional[IpcBuffer] = None
+        if mode == "p2p":
+            try:
+                self._setup_p2p()
+            except Exception as e:  # no IPC / no peer access: fall back to the NCCL exchange
+                self.mode = "nccl"
+                self._fallback_reason = repr(e)
+        if self.mode == "nccl":
+            cp = J.colptr.cpu().numpy() if isinstance(J.colptr, torch.Tensor) else np.asarray(J.colptr)
+            cv = cache.colorvec
+            cv = cv.cpu().numpy() if isinstance(cv, torch.Tensor) else np.asarray(list(cv) if isinstance(cv, range) else cv)
+            self.gp = GatherPlan(entry_colors_csc(cp, cv), self.plan.color_owner(), self.world, self.device)
+
+    def _setup_p2p(self):
+        nnz = self.J.nzval.numel()
+        self._ipc = IpcBuffer(nnz, self.device)
+        self._ipc.tensor.copy_(self.J.nzval)
+        self.J.nzval = self._ipc.tensor                 # J's values now live in the IPC-exportable buffer
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self._ipc.handle(), group=self.group)
+        ptrs = []
+        with torch.cuda.device(self.device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                L.check(L.lib().fdb_ipc_open(h, C.byref(p)))
+                ptrs.append(p.value)
+        self._peers = ptrs
+        self.plan.set_peers(ptrs)
+        ok = torch.ones(1, device=self.device)
+        dist.all_reduce(ok, group=self.group)
+
+    def run(self, f, x, **kw):
+        if self.mode == "p2p" and self.pre_sync:
+            dist.all_reduce(self.flag, group=self.group)    # nobody may still be reading J (stream-ordered)
+        api.finite_difference_jacobian_(self.J, f, x, self.cache, **kw)
+        if self.mode == "p2p":
+            dist.all_reduce(self.flag, group=self.group)    # every rank's scatter (incl. its peer stores) has completed
+        else:
+            allgather_owned(self.J.nzval, self.gp, self.rank, self.group)
+        return None
+
+    def close(self):
+        if self._peers:
+            self.plan.set_peers([])
+            with torch.cuda.device(self.device):
+                for p in self._peers:
+                    L.lib().fdb_ipc_close(C.c_void_p(p))
+            self._peers = []
+        torch.cuda.synchronize(self.device)
+        if self.group is None or dist.is_initialized():
+            try:
+                dist.barrier(group=self.group)
+            except Exception:
+                pass
+        if self._ipc is not None:
+            self._ipc.free()
+            self._ipc = None

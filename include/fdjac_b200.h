@@ -75,7 +75,8 @@ typedef struct {
   int32_t rank, world;     /* colour partition over GPUs (one process per GPU): this plan handles the colours
                               owned by `rank` of `world`; world<=1 => all colours */
   int32_t partition;       /* 0: round-robin colours; 1: nnz-balanced (LPT) */
-  int32_t reserved;
+  int32_t strategy;        /* CSC scatter: 0 auto; 1 one fused pass over J's storage order; 2 per-colour column lists
+                              launched after each colour's f! (see fdb_plan_info_t.strategy) */
 } fdb_plan_opts;
 
 typedef struct fdb_plan fdb_plan;
@@ -92,6 +93,9 @@ typedef struct {
   int64_t device_bytes;    /* device memory held by the plan */
   int32_t fdtype, jkind, sp_kind, color_bits;
   int64_t alg_bytes_scatter; /* SURVEY.md §8(d) algorithmic bytes of the diff+scatter per Jacobian */
+  int32_t strategy;        /* chosen scatter strategy: 0 fused single pass, 1 per-colour column lists */
+  int32_t lanes;           /* lanes per column of the column-list kernel */
+  double mean_row_jump;    /* mean |row[e+1]-row[e]| over consecutive entries (gather locality metric) */
 } fdb_plan_info_t;
 
 typedef struct {

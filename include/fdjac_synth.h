@@ -6,7 +6,7 @@
  *
  *   fdbs_tridiag : test/coloring_tests.jl:5-13    dx[i] = x[i-1] - 2x[i] + x[i+1]
  *   fdbs_lap5    : test/coloring_tests.jl:99-108  clamped 5-point stencil on a g x g grid (column-major)
- *   fdbs_ellrows : dx[i] = sum_p coef[i,p]*x[cols[i,p]] + 0.1*x[cols[i,0]]^2   
+ *   fdbs_ellrows : dx[i] = sum_p coef[p,i]*x[cols[p,i]] + 0.1*x[cols[0,i]]^2, ELL layout [K][m]   
  *   fdbs_rank1   : dx[i] = x[i]^2 + w[i]*S, S = blocked-sum(x)/n                (SURVEY.md §8d config C5 variant)
  */
 #ifndef FDJAC_SYNTH_H

@@ -7,7 +7,7 @@
  *
  *   tridiag : test/coloring_tests.jl:5-13   dx[i] = x[i-1] - 2x[i] + x[i+1]
  *   lap5    : test/coloring_tests.jl:99-108 5-point clamped stencil on a g x g grid
- *   ellrows : random sparse rows, K entries per row
+ *   ellrows : random sparse rows, K entries per row, ELL layout [K][m]
  *   rank1   : dense Jacobian diag + rank-1 (bit-reproducible variant)
  */
 #include <stdint.h>
@@ -62,17 +62,16 @@ void synth_lap5(void *vctx, double *out, const double *x) {
     }
 }
 
-/* dx[i] = sum_p coef[i,p]*x[cols[i,p]]  (left to right)  + 0.1*x[cols[i,0]]^2 ; cols 0-based, row-major [m][K] */
+/* dx[i] = sum_p coef[p,i]*x[cols[p,i]]  (left to right)  + 0.1*x[cols[0,i]]^2 ; cols 0-based, ELL layout [K][m]
+ * (entry p of row i at index p*m + i) */
 void synth_ellrows(void *vctx, double *dx, const double *x) {
   const synth_ell_ctx *c = (const synth_ell_ctx *)vctx;
-  const int64_t K = c->K;
+  const int64_t K = c->K, m = c->m;
   PAR_FOR(c->nthreads)
-  for (int64_t i = 0; i < c->m; ++i) {
-    const int32_t *cc = c->cols + i * K;
-    const double *aa = c->coef + i * K;
-    double x0 = x[cc[0]];
-    double s = aa[0] * x0;
-    for (int64_t p = 1; p < K; ++p) s = s + aa[p] * x[cc[p]];
+  for (int64_t i = 0; i < m; ++i) {
+    double x0 = x[c->cols[i]];
+    double s = c->coef[i] * x0;
+    for (int64_t p = 1; p < K; ++p) s = s + c->coef[p * m + i] * x[c->cols[p * m + i]];
     s = s + 0.1 * (x0 * x0);
     dx[i] = s;
   }

@@ -1,0 +1,124 @@
+"""Multi-GPU parity (needs >= 2 GPUs: run under `gpurun --gpus 2`; skipped on a single-GPU box).
+One process per GPU (NCCL); colours sharded over the ranks; both exchange modes; every rank must end with the
+complete Jacobian, bit-identical to the single-process CPU oracle fed the device-computed step sizes."""
+import ctypes as C
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ell_problem(n, K, Cc, seed):
+    rng = np.random.default_rng(seed)
+    per = n // Cc
+    colors = np.argsort(rng.random((n, Cc)), axis=1)[:, :K]
+    which = rng.integers(0, per, size=(n, K))
+    cols = (which * Cc + colors).astype(np.int32)
+    coef = rng.uniform(-1, 1, size=(n, K))
+    return cols, coef
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import scipy.sparse as sps
+        import _bootstrap
+        pkg = _bootstrap.load_package()
+        from finitediff_jl_b200 import distributed as fdist
+        from oracle import fd_oracle as orc
+        L = pkg._lib
+        n, K, Cc = 64 * 300, 8, 64
+        cols, coef = _ell_problem(n, K, Cc, 11)
+        A = sps.csc_matrix((np.ones(n * K), (np.repeat(np.arange(n), K), cols.reshape(-1))), shape=(n, n))
+        A.sort_indices()
+        colptr, rowval = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1
+        cv = (np.arange(n, dtype=np.int64) % Cc) + 1
+        xh = orc.fill_x(n, 77)
+        colsT, coefT = np.ascontiguousarray(cols.T), np.ascontiguousarray(coef.T)   # ELL layout [K][m]
+        d_cols, d_coef = torch.from_numpy(colsT).to(dev), torch.from_numpy(coefT).to(dev)
+        octx = orc.SynthEllCtx(n, K, colsT.ctypes.data_as(C.POINTER(C.c_int32)), coefT.ctypes.data_as(C.POINTER(C.c_double)), 1)
+        for fdtype in ("forward", "central"):
+            for mode in ("p2p", "nccl"):
+                for partition in (0, 1):
+                    x = torch.from_numpy(xh).to(dev)
+                    J = pkg.SparseMatrixCSC(n, n, torch.from_numpy(colptr), torch.from_numpy(rowval),
+                                            torch.full((A.nnz,), float("nan"), dtype=torch.float64, device=dev))
+                    ctx = L.EllCtx(n, K, d_cols.data_ptr(), d_coef.data_ptr(), 0)
+                    f = pkg.NativeFn(C.cast(L.synth().fdbs_ellrows, C.c_void_p).value, ctx)
+                    cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, rank=rank, world=world, partition=partition)
+                    sh = fdist.ShardedJacobian(J, cache, n, dev, mode=mode)
+                    assert sh.mode == mode, getattr(sh, "_fallback_reason", "")
+                    for _ in range(2):
+                        sh.run(f, x)
+                    torch.cuda.synchronize()
+                    plan = cache._last_plan
+                    info = plan.info()
+                    ec = fdist.entry_colors_csc(colptr, cv)
+                    counts = np.bincount(ec, minlength=Cc)
+                    assert np.array_equal(plan.color_owner(), fdist.partition_colors(Cc, world, counts, partition))
+                    assert info["n_local_colors"] == int((plan.color_owner() == rank).sum())
+                    eps = plan.eps()
+                    ref = np.full(A.nnz, np.nan)
+                    orc.jacobian(orc.Problem.csc_same(n, n, colptr, rowval), ref, orc.native_fn("synth_ellrows"), xh.copy(),
+                                 fdtype=0 if fdtype == "forward" else 1, colorvec=cv, eps_override=eps, ctx=octx)
+                    got = J.nzval.cpu().numpy()
+                    assert np.array_equal(got, ref), f"rank {rank} {fdtype} {mode} partition={partition}"
+                    per_call = ctx.calls // 2
+                    assert per_call == (info["n_local_colors"] + 1 if fdtype == "forward" else 2 * info["n_local_colors"])
+                    sh.close()
+        # dense column-sharded plan: each rank computes its column slab
+        nd = 257
+        w = np.random.default_rng(2).random(nd)
+        d_w = torch.from_numpy(w).to(dev)
+        bs = torch.zeros(8, dtype=torch.float64, device=dev)
+        xd = orc.fill_x(nd, 5)
+        x = torch.from_numpy(xd).to(dev)
+        ctx = L.Rank1Ctx(nd, d_w.data_ptr(), bs.data_ptr(), 4, 0)
+        o = L.PlanOpts(fdtype=1, device=rank, max_batch=4, rank=rank, world=world)
+        h = C.c_void_p()
+        L.check(L.lib().fdb_plan_create_dense(C.byref(h), nd, nd, nd, C.byref(o)))
+        plan = pkg.Plan(h.value)
+        b, e = plan.dense_range()
+        Jslab = torch.full((nd * (e - b),), float("nan"), dtype=torch.float64, device=dev)
+        L.check(L.lib().fdb_jacobian(plan.handle, C.cast(L.synth().fdbs_rank1, C.c_void_p), C.cast(C.pointer(ctx), C.c_void_p),
+                                     x.data_ptr(), Jslab.data_ptr(), None, None, 0.0, 0.0, 1.0, None))
+        torch.cuda.synchronize()
+        ref = np.zeros(nd * nd)
+        orc.jacobian(orc.Problem.dense(nd, nd), ref, orc.native_fn("synth_rank1"), xd.copy(), fdtype=1,
+                     ctx=orc.SynthRank1Ctx(nd, w.ctypes.data_as(C.POINTER(C.c_double)), 1))
+        assert np.array_equal(Jslab.cpu().numpy(), ref[b * nd: e * nd]), f"rank {rank} dense slab"
+        assert ctx.calls == 2 * (e - b)
+        (Path(out_dir) / f"ok_{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_colors(tmp_path, oracle):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok_{r}").exists() for r in range(world))

@@ -48,7 +48,7 @@ def t64(a, device=None):
 
 
 def run_csc_tridiag(pkg, oracle, dev, N, fdtype, *, no_drift=False, max_batch=1, scratch_bytes=0, index_on_device=False,
-                    colors=3):
+                    colors=3, strategy=0):
     colptr, rowval = tridiag_csc(N)
     cv = cyc_colors(N, colors)
     x = dev_x(pkg, dev, N, 0x5EED + 2)
@@ -58,7 +58,7 @@ def run_csc_tridiag(pkg, oracle, dev, N, fdtype, *, no_drift=False, max_batch=1,
     ctx = pkg._lib.TridiagCtx(N, 0)
     f = native(pkg, "fdbs_tridiag", ctx, max_batch)
     cache = pkg.JacobianCache(x, fdtype, colorvec=t64(cv, idev) if index_on_device else cv, sparsity=J,
-                              no_drift=no_drift, max_batch=max_batch, scratch_bytes=scratch_bytes)
+                              no_drift=no_drift, max_batch=max_batch, scratch_bytes=scratch_bytes, strategy=strategy)
     x_before = x.clone()
     pkg.finite_difference_jacobian_(J, f, x, cache)
     torch.cuda.synchronize()
@@ -106,12 +106,27 @@ def test_tridiag_index_arrays_on_device(pkg, oracle, dev):
 def test_tridiag_multi_group_and_batch(pkg, oracle, dev, fdtype):
     # 7 colours, scratch budget for ~2 slabs -> several scatter launches; batched f! (3 points per callback)
     N = 20000
-    a = run_csc_tridiag(pkg, oracle, dev, N, fdtype, colors=7, scratch_bytes=8 * (N + 2) * (4 if fdtype == "central" else 2) + 64)
-    assert a[6].info()["n_groups"] > 1
+    small = 8 * (N + 2) * (4 if fdtype == "central" else 2) + 64
+    a = run_csc_tridiag(pkg, oracle, dev, N, fdtype, colors=7, scratch_bytes=small, strategy=1)   # fused pass per group
+    assert a[6].info()["n_groups"] > 1 and a[6].info()["strategy"] == 0
+    assert np.array_equal(a[0], a[1])
+    a = run_csc_tridiag(pkg, oracle, dev, N, fdtype, colors=7, scratch_bytes=small)               # auto -> column lists
+    assert a[6].info()["n_groups"] > 1 and a[6].info()["strategy"] == 1
     assert np.array_equal(a[0], a[1])
     b = run_csc_tridiag(pkg, oracle, dev, N, fdtype, colors=7, max_batch=3)
     assert np.array_equal(b[0], b[1])
     assert b[4] == b[5]
+
+
+@pytest.mark.parametrize("fdtype", ["forward", "central"])
+def test_per_colour_list_strategy_tridiag(pkg, oracle, dev, fdtype):
+    # strategy 2: per-colour column lists (ext/FiniteDiffSparseArraysExt.jl:38-47 shape), several colours per launch,
+    # more colours than kMaxSegs, odd sizes, batched f!
+    for N, colors, mb in ((4099, 3, 1), (10000, 19, 1), (10000, 19, 4), (7, 3, 1)):
+        got, ref, eps, eps_o, calls, ocalls, plan = run_csc_tridiag(pkg, oracle, dev, N, fdtype, colors=colors, strategy=2,
+                                                                    max_batch=mb)
+        assert plan.info()["strategy"] == 1 and calls == ocalls
+        assert np.array_equal(got, ref)
 
 
 def test_c2_full_size_bitexact(pkg, oracle, dev):
@@ -429,8 +444,10 @@ def ell_problem(n, K, C, seed):
 
 
 @pytest.mark.parametrize("fdtype", ["forward", "central"])
-def test_c4_random_sparse_64_colors_bitexact(pkg, oracle, dev, fdtype):
-    """BASELINE config C4 shape at reduced n: random sparse f!, 8 nnz/row, 64 colours, CSC J."""
+@pytest.mark.parametrize("strategy", [1, 2])
+def test_c4_random_sparse_64_colors_bitexact(pkg, oracle, dev, fdtype, strategy):
+    """BASELINE config C4 shape at reduced n: random sparse f!, 8 nnz/row, 64 colours, CSC J — through BOTH scatter
+    strategies: 1 = one fused pass over nzval, 2 = per-colour column lists launched after each colour's f!."""
     import scipy.sparse as sps
     n, K, Cc = 64 * 400, 8, 64
     cols, coef = ell_problem(n, K, Cc, 11)
@@ -440,14 +457,17 @@ def test_c4_random_sparse_64_colors_bitexact(pkg, oracle, dev, fdtype):
     cv = cyc_colors(n, Cc)
     x = dev_x(pkg, dev, n, 0x5EED + 4)
     xh = oracle.fill_x(n, 0x5EED + 4)
-    d_cols = torch.from_numpy(cols).to(dev)
-    d_coef = torch.from_numpy(coef).to(dev)
+    colsT, coefT = np.ascontiguousarray(cols.T), np.ascontiguousarray(coef.T)     # ELL layout [K][m]
+    d_cols = torch.from_numpy(colsT).to(dev)
+    d_coef = torch.from_numpy(coefT).to(dev)
     ctx = pkg._lib.EllCtx(n, K, d_cols.data_ptr(), d_coef.data_ptr(), 0)
     J = pkg.SparseMatrixCSC(n, n, t64(colptr), t64(rowval), torch.full((A.nnz,), float("nan"), dtype=torch.float64, device=dev))
-    cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J)
+    cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, strategy=strategy)
     pkg.finite_difference_jacobian_(J, native(pkg, "fdbs_ellrows", ctx), x, cache)
     eps = cache._last_plan.eps()
-    octx = oracle.SynthEllCtx(n, K, cols.ctypes.data_as(C.POINTER(C.c_int32)), coef.ctypes.data_as(C.POINTER(C.c_double)), 1)
+    info = cache._last_plan.info()
+    assert info["strategy"] == strategy - 1 and info["mean_row_jump"] > 64
+    octx = oracle.SynthEllCtx(n, K, colsT.ctypes.data_as(C.POINTER(C.c_int32)), coefT.ctypes.data_as(C.POINTER(C.c_double)), 1)
     ref = np.full(A.nnz, np.nan)
     r = oracle.jacobian(oracle.Problem.csc_same(n, n, colptr, rowval), ref, oracle.native_fn("synth_ellrows"), xh.copy(),
                         fdtype=FD[fdtype], colorvec=cv, eps_override=eps, ctx=octx)
@@ -503,13 +523,16 @@ def test_invalid_and_empty_colours(pkg, oracle, dev):
     for fdtype in ("forward", "central"):
         J = pkg.SparseMatrixCSC(N, N, t64(colptr), t64(rowval), torch.full((len(rowval),), float("nan"), dtype=torch.float64, device=dev))
         ctx = pkg._lib.TridiagCtx(N, 0)
-        cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J)
-        pkg.finite_difference_jacobian_(J, native(pkg, "fdbs_tridiag", ctx), x, cache)
-        ref = np.full(len(rowval), np.nan)
-        r = oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"), xh.copy(),
-                            fdtype=FD[fdtype], colorvec=cv, eps_override=cache._last_plan.eps(), ctx=oracle.SynthTridiagCtx(N, 1))
-        assert ctx.calls == r["fcalls"] == (5 if fdtype == "forward" else 8)
-        assert np.array_equal(J.nzval.cpu().numpy(), ref)
+        for strategy in (1, 2):
+            J.nzval.fill_(float("nan"))
+            ctx.calls = 0
+            cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, strategy=strategy)
+            pkg.finite_difference_jacobian_(J, native(pkg, "fdbs_tridiag", ctx), x, cache)
+            ref = np.full(len(rowval), np.nan)
+            r = oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"), xh.copy(),
+                                fdtype=FD[fdtype], colorvec=cv, eps_override=cache._last_plan.eps(), ctx=oracle.SynthTridiagCtx(N, 1))
+            assert ctx.calls == r["fcalls"] == (5 if fdtype == "forward" else 8)
+            assert np.array_equal(J.nzval.cpu().numpy(), ref)
 
 
 def test_different_pattern_csc_J(pkg, oracle, dev):
