@@ -228,7 +228,7 @@ def workload_name(w, fdtype):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
+def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch, use_graph=True):
     """Returns dict(J, f, x, cache, nnz, fcalls, f_launches_per_call, keep)."""
     import torch
     L = pkg._lib
@@ -246,7 +246,8 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
         J = pkg.SparseMatrixCSC(n, n, colptr, rowval, torch.full((3 * n - 2,), float("nan"), dtype=torch.float64, device=dev))
         ctx = L.TridiagCtx(n, 0)
         f = native("fdbs_tridiag", ctx, max_batch)
-        cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch, rank=rank, world=world)
+        cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch, rank=rank, world=world,
+                                  use_graph=use_graph)
         return dict(J=J, f=f, x=x, cache=cache, nnz=3 * n - 2, n=n, ctx=ctx, keep=(colptr, rowval, cv))
     if workload == "c4":
         n, K, Cc = 5_000_000, 8, 64
@@ -274,7 +275,7 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
         ctx = L.EllCtx(n, K, d_cols.data_ptr(), d_coef.data_ptr(), 0)
         f = native("fdbs_ellrows", ctx, max_batch)
         cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch, rank=rank, world=world,
-                                  partition=0)
+                                  partition=0, use_graph=use_graph)
         return dict(J=J, f=f, x=x, cache=cache, nnz=n * K, n=n, ctx=ctx, keep=(d_cols, d_coef, cv))
     if workload == "c3":
         g = 1000
@@ -286,11 +287,11 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
         J = pkg.BandedMatrix(n, n, g, g, device=dev)
         ctx = L.Lap5Ctx(g, 0)
         f = native("fdbs_lap5", ctx, max_batch)
-        cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch)
+        cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch, use_graph=use_graph)
         return dict(J=J, f=f, x=x, cache=cache, nnz=None, n=n, ctx=ctx, keep=(cv,))
     if workload == "c5":
         n = 100_000 if world == 1 else 100_000
-        mb = max(max_batch, 64)
+        mb = max(max_batch, 256)
         w = torch.rand(n, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
         nblk = (n + 1023) // 1024
         bs = torch.zeros(nblk * mb, dtype=torch.float64, device=dev)
@@ -300,7 +301,7 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch):
         f = native("fdbs_rank1", ctx, mb)
         if world != 1:
             raise SystemExit("c5 is benchmarked at --gpus 1 here (column-sharded runs: tests/test_gpu_multi.py)")
-        cache = pkg.JacobianCache(x, fdtype, max_batch=mb)
+        cache = pkg.JacobianCache(x, fdtype, max_batch=mb, use_graph=use_graph)
         J = pkg.zeros_colmajor(n, n, dev)
         return dict(J=J, f=f, x=x, cache=cache, nnz=n * n, n=n, ctx=ctx, keep=(w, bs))
     raise SystemExit(f"unknown workload {workload}")
@@ -323,7 +324,7 @@ def gpu_arm(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     workload, fdtype = args.workload, args.fdtype
-    prob = build_gpu_problem(pkg, workload, fdtype, dev, rank, world, args.max_batch)
+    prob = build_gpu_problem(pkg, workload, fdtype, dev, rank, world, args.max_batch, args.graph)
     J, f, x, cache = prob["J"], prob["f"], prob["x"], prob["cache"]
 
     sharded = None
@@ -349,9 +350,6 @@ def gpu_arm(args):
     info = plan.info()
     nnz = prob["nnz"] if prob["nnz"] is not None else info["n_entries"]
     c0 = plan.counters()
-    f0 = prob["ctx"].calls
-    plan.enable_timing(True)
-    plan.read_timing()
     clocks = Clocks(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -366,10 +364,18 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     clk = clocks.stop() if clocks else None
+    c1 = plan.counters()
+    f_points = c1["f_points"] - c0["f_points"]
+    # the dominant kernel, timed live with CUDA events recorded by the library around its launch (eager launches:
+    # events recorded inside a captured graph cannot be timed) — same stream, right after the timed region
+    tsteps = args.steps
+    plan.enable_timing(True)
+    plan.read_timing()
+    for _ in range(tsteps):
+        step()
+    barrier()
     scat_ms, scat_n = plan.read_timing()
     plan.enable_timing(False)
-    c1 = plan.counters()
-    f_points = prob["ctx"].calls - f0
     f_launch_per_point = {"c5": 2}.get(workload, 1)
     lib_launches = c1["kernel_launches"] - c0["kernel_launches"]
     f_invocations = c1["f_invocations"] - c0["f_invocations"]
@@ -389,15 +395,27 @@ def gpu_arm(args):
     alg_bytes = info["alg_bytes_scatter"]
     if world > 1 and workload != "c5":
         alg_bytes = alg_bytes * info["n_local_colors"] // max(info["n_colors"], 1)
-    scat_per_jac = scat_ms / args.steps if args.steps else 0.0
+    scat_per_jac = scat_ms / tsteps if tsteps else 0.0
+    launches_per_jac = scat_n / tsteps if tsteps else 0
     achieved = alg_bytes / (scat_per_jac * 1e-3) / 1e9 if scat_per_jac > 0 else None
-    roofline = {"bound": "hbm", "kernel": "diff_scatter_ident<uint8,forward>" if workload in ("c1", "c2", "c4") else "diff_scatter",
+    if info["sp_kind"] == 1:
+        kname = ("diff_scatter_cols<%s,%d lanes>" % (fdtype, info["lanes"]) if info["strategy"] == 1
+                 else "diff_scatter_ident<u%d,%s,FULL>" % (info["color_bits"], fdtype))
+    else:
+        kname = {4: "diff_scatter_band", 0: "diff_columns", 3: "diff_scatter_dest"}.get(info["sp_kind"], "diff_scatter")
+    traffic = args.traffic_bytes
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": args.traffic_bytes, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes / launches_per_jac if launches_per_jac else None,
+                "launch_ms": scat_per_jac / launches_per_jac if launches_per_jac else None,
                 "alg_bytes_per_jacobian": alg_bytes, "scatter_ms_per_jacobian": scat_per_jac,
-                "scatter_launches_per_jacobian": scat_n / args.steps if args.steps else None,
-                "note": "achieved uses SURVEY.md §8(d) algorithmic bytes (Int64 indices, fx re-read per nonzero); the fused "
-                        "kernel moves fewer real bytes (int32 rows + uint8 colours, fx[r] cached) — see `traffic` / DESIGN.md"}
+                "scatter_launches_per_jacobian": launches_per_jac,
+                "frac_moved": (traffic * launches_per_jac / (scat_per_jac * 1e-3) / 1e9 / peak) if (traffic and scat_per_jac > 0) else None,
+                "note": "achieved = SURVEY.md §8(d) algorithmic bytes (Int64 indices at the ABI, fx re-read per nonzero) / "
+                        "CUDA-event time of the scatter launches; the fused kernel moves fewer real bytes (int32 rows + narrow "
+                        "colours, fx[r] served from cache): `traffic` = ncu dram bytes per launch, `frac_moved` = traffic-based "
+                        "fraction of the same peak"}
 
     # ---- e2e: host buffers through the C ABI (fdb_jacobian_host), H2D x + D2H J values inside the timed region
     e2e = None
@@ -440,7 +458,7 @@ def gpu_arm(args):
             "metric": "jacobian_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(workload, fdtype), "l2": "inputs larger than L2 (no flush needed): x, the stacked "
+            "config": {"workload": workload_name(workload, fdtype), "cuda_graph": bool(args.graph), "l2": "inputs larger than L2 (no flush needed): x, the stacked "
                        "f! outputs and nzval total far more than 126 MB per step" if workload != "c1" else "C1 is L2-resident (latency config)",
                        "max_batch": args.max_batch, "colors_local": info["n_local_colors"], "scatter_groups": info["n_groups"]},
             "f_evals_per_s": f_points_all / (ms_total * 1e-3),
@@ -463,6 +481,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--fdtype", default="forward", choices=["forward", "central"])
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch eagerly instead of replaying the captured CUDA graph of the call")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scale", type=float, default=None, dest="cpu_scale",

@@ -26,6 +26,7 @@ class PlanOpts(C.Structure):
         ("fdtype", C.c_int32), ("device", C.c_int32), ("use_current_device", C.c_int32), ("no_drift", C.c_int32),
         ("max_batch", C.c_int64), ("scratch_bytes", C.c_int64),
         ("rank", C.c_int32), ("world", C.c_int32), ("partition", C.c_int32), ("strategy", C.c_int32),
+        ("use_graph", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -339,10 +339,10 @@ class Plan:
 
 
 def _opts(fdtype, device_index, *, no_drift=False, max_batch=1, scratch_bytes=0, rank=0, world=1, partition=0,
-          strategy=0):
+          strategy=0, use_graph=False):
     return L.PlanOpts(fdtype=fdtype, device=device_index, use_current_device=0, no_drift=int(bool(no_drift)),
                       max_batch=int(max_batch), scratch_bytes=int(scratch_bytes), rank=int(rank), world=int(world),
-                      partition=int(partition), strategy=int(strategy))
+                      partition=int(partition), strategy=int(strategy), use_graph=int(bool(use_graph)), reserved=0)
 
 
 def _device_index(device) -> int:

@@ -68,6 +68,19 @@ struct DeviceGuard {
   }
 };
 
+// identity of a captured call: same function, buffers and scalar arguments => same launch sequence
+struct GraphKey {
+  void *f = nullptr, *ctx = nullptr;
+  const void *x = nullptr, *J = nullptr, *fx = nullptr, *f_in = nullptr;
+  double relstep = 0, absstep = 0, dir = 0;
+  int n_peers = 0;
+  long long peer_generation = 0;
+  bool operator==(const GraphKey &o) const {
+    return f == o.f && ctx == o.ctx && x == o.x && J == o.J && fx == o.fx && f_in == o.f_in && relstep == o.relstep &&
+           absstep == o.absstep && dir == o.dir && n_peers == o.n_peers && peer_generation == o.peer_generation;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ plan
 struct fdb_plan {
   int device = 0, sm_count = 148;
@@ -119,6 +132,13 @@ struct fdb_plan {
   fdb_counters_t cnt{};
   int64_t alg_bytes = 0;
   int64_t last_eps_count = 0;
+  // optional CUDA-graph replay of the whole call
+  bool use_graph = false;
+  cudaStream_t cstream = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;
+  fdb_counters_t graph_delta{};
+  long long peer_generation = 0;
   // optional device-side timing of the scatter launches
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_pool;
@@ -339,6 +359,7 @@ static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, in
   P->n = n;
   P->fdtype = o ? o->fdtype : FDB_FORWARD;
   P->no_drift = o ? o->no_drift : 0;
+  P->use_graph = o && o->use_graph != 0;
   P->world = (o && o->world > 1) ? o->world : 1;
   P->rank = (o && o->world > 1) ? o->rank : 0;
   if (P->rank < 0 || P->rank >= P->world) { delete P; return fail(FDB_ERR_INVALID, "rank %d outside world %d", P->rank, P->world); }
@@ -357,6 +378,8 @@ static void free_plan(fdb_plan *P) {
   for (auto &ev : P->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto &ev : P->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (P->hstream) cudaStreamDestroy(P->hstream);
+  if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
+  if (P->cstream) cudaStreamDestroy(P->cstream);
   delete P;
 }
 
@@ -775,6 +798,7 @@ fdb_status fdb_plan_set_peers(fdb_plan *P, int n_peers, double *const *peer_J) {
   if (!P->d_peers) TRY(P->alloc_t(&P->d_peers, 64));
   if (n_peers > 0) CU(cudaMemcpy(P->d_peers, peer_J, (size_t)n_peers * sizeof(double *), cudaMemcpyHostToDevice));
   P->n_peers = n_peers;
+  P->peer_generation += 1;
   P->peers_aligned = true;
   for (int i = 0; i < n_peers; ++i)
     if (reinterpret_cast<uintptr_t>(peer_J[i]) & 15) P->peers_aligned = false;
@@ -961,7 +985,15 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       int64_t ntiles;
       if (w >= 512) { a.chunks_per_col = (w + kThreads * 4 - 1) / (kThreads * 4); a.cols_per_tile = 0; ntiles = P->n * a.chunks_per_col; }
       else { a.chunks_per_col = 0; a.cols_per_tile = std::max<int64_t>(1, 4096 / w); ntiles = (P->n + a.cols_per_tile - 1) / a.cols_per_tile; }
-      if (ntiles > 0) {
+      if (w >= 64 && P->n > 0) {
+        // wide band: one warp per column
+        const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
+        const int grid = resident_grid(P, diff_scatter_band_wide<CT, CENTRAL>, sm, (P->n + 7) / 8);
+        ScatterTimer tm(P, s);
+        diff_scatter_band_wide<CT, CENTRAL><<<grid, kThreads, sm, s>>>(a);
+        P->cnt.kernel_launches += 1;
+        P->cnt.scatter_launches += 1;
+      } else if (ntiles > 0) {
         const int blocks = (int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16);
         ScatterTimer tm(P, s);
         diff_scatter_band<CT, CENTRAL><<<blocks, kThreads, 0, s>>>(a);
@@ -1065,6 +1097,20 @@ static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, d
 
 extern "C" {
 
+static fdb_status jacobian_eager(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, double *d_J, double *fx,
+                                 const double *d_f_in, double relstep, double absstep, double dir, cudaStream_t s) {
+  if (P->sp_kind == SP_NONE) {
+    return P->fdtype == FDB_CENTRAL ? run_dense<true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
+                                    : run_dense<false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+  }
+  return dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+    using CT = decltype(tag);
+    return P->fdtype == FDB_CENTRAL
+               ? run_colored<CT, true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
+               : run_colored<CT, false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+  });
+}
+
 fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, double *d_J, double *d_fx,
                         const double *d_f_in, double relstep, double absstep, double dir, void *stream) {
   if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
@@ -1077,16 +1123,43 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
   if (!(absstep > 0)) absstep = relstep;
   double *fx = d_fx ? d_fx : P->fx_own;
   fdb_status st;
-  if (P->sp_kind == SP_NONE) {
-    st = P->fdtype == FDB_CENTRAL ? run_dense<true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
-                                  : run_dense<false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+  if (P->use_graph && !P->timing) {
+    // CUDA-graph replay of the whole call: the launch sequence depends only on the plan and on these arguments
+    // (the step sizes are computed on the device inside the graph), so it is captured once and re-launched.
+    const GraphKey key{(void *)f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, P->n_peers, P->peer_generation};
+    if (!P->graph_exec || !(key == P->graph_key)) {
+      if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
+      if (!P->cstream) CU(cudaStreamCreateWithFlags(&P->cstream, cudaStreamNonBlocking));
+      const fdb_counters_t before = P->cnt;
+      CU(cudaStreamBeginCapture(P->cstream, cudaStreamCaptureModeThreadLocal));
+      st = jacobian_eager(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, P->cstream);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(P->cstream, &graph);
+      if (st != FDB_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return st; }
+      if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        return fail(FDB_ERR_CUDA, "stream capture of the Jacobian failed (%s): the f! callback must be capture-safe "
+                                  "(enqueue-only, no allocation) when use_graph is set", cudaGetErrorString(e));
+      }
+      e = cudaGraphInstantiate(&P->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { P->graph_exec = nullptr; return fail(FDB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+      P->graph_key = key;
+      // what one replay amounts to (the capture pass itself launched nothing)
+      P->graph_delta.f_points = P->cnt.f_points - before.f_points;
+      P->graph_delta.f_invocations = P->cnt.f_invocations - before.f_invocations;
+      P->graph_delta.kernel_launches = P->cnt.kernel_launches - before.kernel_launches;
+      P->graph_delta.scatter_launches = P->cnt.scatter_launches - before.scatter_launches;
+      P->cnt = before;
+    }
+    CU(cudaGraphLaunch(P->graph_exec, s));
+    P->cnt.f_points += P->graph_delta.f_points;
+    P->cnt.f_invocations += P->graph_delta.f_invocations;
+    P->cnt.kernel_launches += P->graph_delta.kernel_launches;
+    P->cnt.scatter_launches += P->graph_delta.scatter_launches;
+    st = FDB_OK;
   } else {
-    st = dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
-      using CT = decltype(tag);
-      return P->fdtype == FDB_CENTRAL
-                 ? run_colored<CT, true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
-                 : run_colored<CT, false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
-    });
+    st = jacobian_eager(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
   }
   if (st == FDB_OK) P->cnt.jacobians += 1;
   return st;

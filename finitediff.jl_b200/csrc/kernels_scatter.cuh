@@ -268,6 +268,70 @@ struct BandArgs {
   int64_t cols_per_tile, chunks_per_col;   // tiling of the (l+u+1) x n band
 };
 
+// Wide bands (l+u+1 >= 64): ONE WARP PER COLUMN.  A band column is a contiguous run of l+u+1 slots whose sources
+// F[slab][c-u .. c+l] are contiguous too; the warp walks it 32 slots at a time (256-byte coalesced stores, coalesced
+// L2-resident gathers), 4 steps in flight.  The per-column work (colour -> slab, eps) is one uniform lookup from
+// shared-memory tables, amortised over the whole column (r1: the per-1024-slot tile version spent most of its time in
+// that dependent-load prologue: 8.1 ms for C3; see profiles/).
+template <typename CT, bool CENTRAL>
+__global__ void __launch_bounds__(kThreads)
+diff_scatter_band_wide(const BandArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *s_eps = reinterpret_cast<double *>(smem);
+  int32_t *s_slab = reinterpret_cast<int32_t *>(smem + sizeof(double) * (a.C <= kSmemTable ? a.C : 0));
+  const bool tables = a.C <= kSmemTable;
+  if (tables) {
+    for (int i = threadIdx.x; i < a.C; i += kThreads) {
+      const int32_t lo = a.local_of[i];
+      int32_t sl = lo < 0 ? -1 : lo - a.l0;
+      if (sl >= a.G) sl = -1;
+      s_slab[i] = sl;
+      s_eps[i] = a.eps[i];
+    }
+    __syncthreads();
+  }
+  const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
+  const int lane = threadIdx.x & 31;
+  const int64_t w = a.l + a.u + 1;
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t c = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < a.n; c += nwarps) {
+    const uint32_t k = (uint32_t)jcolor[c];
+    int32_t slab = -1;
+    double e = 1.0;
+    if (k < (uint32_t)a.C) {
+      if (tables) { slab = s_slab[k]; e = s_eps[k]; }
+      else {
+        const int32_t lo = __ldg(a.local_of + k);
+        slab = lo < 0 ? -1 : lo - a.l0;
+        if (slab >= a.G) slab = -1;
+        e = __ldg(a.eps + k);
+      }
+    }
+    const bool owned = slab >= 0;
+    const bool zero_col = k >= (uint32_t)a.C && a.write_other && !a.to_dense;   // no valid colour: stays 0 (fill_matrix!)
+    if (!owned && !zero_col) continue;                                         // another group's / rank's column
+    const double denom = CENTRAL ? 2 * e : e;
+    const double *__restrict__ hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF + (c - a.u);
+    const double *__restrict__ lo = (CENTRAL ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx) + (c - a.u);
+    // in-matrix slots: rows r = c-u+d in [0, m)  <=>  d in [d_lo, d_hi)
+    const int64_t d_lo = a.u - c > 0 ? a.u - c : 0;
+    const int64_t d_hi = a.m - c + a.u < w ? a.m - c + a.u : w;
+    if (a.to_dense) {
+      double *__restrict__ out = a.J + c * a.ldJ + (c - a.u);
+      if (owned)
+        for (int64_t d = d_lo + lane; d < d_hi; d += 32) out[d] = (__ldg(hi + d) - __ldg(lo + d)) / denom;
+    } else {
+      double *__restrict__ out = a.J + c * w;
+#pragma unroll 4
+      for (int64_t d = lane; d < w; d += 32) {
+        double v = 0.0;                                    // corner slots outside the matrix get 0
+        if (owned && d >= d_lo && d < d_hi) v = (__ldg(hi + d) - __ldg(lo + d)) / denom;
+        st_stream(out + d, v);
+      }
+    }
+  }
+}
+
 template <typename CT, bool CENTRAL>
 __global__ void __launch_bounds__(kThreads)
 diff_scatter_band(const BandArgs a) {

@@ -72,12 +72,21 @@ __global__ void __launch_bounds__(kT) k_ellrows(double *__restrict__ fx, const d
 // blocked sum: blocks of 1024 summed sequentially (one thread each — tiny), then block sums sequentially
 __global__ void __launch_bounds__(kT) k_block_sums(const double *__restrict__ x, int64_t n, int64_t ldx,
                                                    double *__restrict__ bs, int64_t nblk) {
+  // one warp per 1024-block: lane l sums x[b + l + 32 j] (j ascending, coalesced), xor butterfly — the order of
+  // oracle/synth_fns.c:synth_blocked_sum
   const double *xb = x + (int64_t)blockIdx.y * ldx;
-  for (int64_t b = blockIdx.x * (int64_t)kT + threadIdx.x; b < nblk; b += (int64_t)gridDim.x * kT) {
-    const int64_t s0 = b * 1024, e0 = s0 + 1024 < n ? s0 + 1024 : n;
+  const int lane = threadIdx.x & 31;
+  for (int64_t b = blockIdx.x * (int64_t)(kT / 32) + (threadIdx.x >> 5); b < nblk; b += (int64_t)gridDim.x * (kT / 32)) {
+    const int64_t s0 = b * 1024;
     double s = 0.0;
-    for (int64_t j = s0; j < e0; ++j) s = add(s, xb[j]);
-    bs[(int64_t)blockIdx.y * nblk + b] = s;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int64_t idx = s0 + lane + 32 * j;
+      s = add(s, idx < n ? xb[idx] : 0.0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = add(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == 0) bs[(int64_t)blockIdx.y * nblk + b] = s;
   }
 }
 
@@ -164,7 +173,7 @@ int fdbs_rank1(void *vctx, double *d_fx, const double *d_x, int64_t batch, int64
   c->calls += batch;
   if (c->n <= 0) return 0;
   const int64_t nblk = (c->n + 1023) / 1024;
-  dim3 g1((unsigned)blocks_for(nblk, 64), (unsigned)batch);
+  dim3 g1((unsigned)blocks_for(nblk * 32, 64), (unsigned)batch);   // one warp per 1024-block
   k_block_sums<<<g1, kT, 0, (cudaStream_t)stream>>>(d_x, c->n, ldx, c->d_block_sums, nblk);
   dim3 g2((unsigned)blocks_for(c->n, 64), (unsigned)batch);
   k_rank1<<<g2, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, c->d_w, c->d_block_sums, nblk, ldfx, ldx);

@@ -30,9 +30,11 @@ struct PlanOpts
     world::Int32
     partition::Int32
     strategy::Int32
+    use_graph::Int32
+    reserved::Int32
 end
 PlanOpts(fd; max_batch = 1, rank = 0, world = 1) =
-    PlanOpts(fd, 0, 1, 0, max_batch, 0, rank, world, 0, 0)
+    PlanOpts(fd, 0, 1, 0, max_batch, 0, rank, world, 0, 0, 0, 0)
 
 struct FdbError <: Exception
     status::Cint

@@ -81,12 +81,25 @@ void synth_ellrows(void *vctx, double *dx, const double *x) {
  * (blocks of 1024 summed sequentially, block sums summed sequentially) so CPU and GPU agree bitwise.
  * Jacobian = diag(2 x_i) + w * 1^T / n  (dense). */
 double synth_blocked_sum(const double *x, int64_t n) {
+  /* warp-shaped order (so the CUDA twin can read coalesced): per block of 1024, 32 lane partials
+   * p[l] = sum_j x[b + l + 32 j] (j ascending; elements past n count as 0), then the xor butterfly
+   * p[l] += p[l^o], o = 16,8,4,2,1; block sums are added in block order. */
   double total = 0.0;
   for (int64_t b = 0; b < n; b += 1024) {
-    int64_t e = b + 1024 < n ? b + 1024 : n;
-    double s = 0.0;
-    for (int64_t j = b; j < e; ++j) s = s + x[j];
-    total = total + s;
+    double p[32], q[32];
+    for (int l = 0; l < 32; ++l) {
+      double s = 0.0;
+      for (int j = 0; j < 32; ++j) {
+        int64_t idx = b + l + 32 * (int64_t)j;
+        s = s + (idx < n ? x[idx] : 0.0);
+      }
+      p[l] = s;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ o];
+      for (int l = 0; l < 32; ++l) p[l] = q[l];
+    }
+    total = total + p[0];
   }
   return total;
 }

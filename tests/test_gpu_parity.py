@@ -129,6 +129,50 @@ def test_per_colour_list_strategy_tridiag(pkg, oracle, dev, fdtype):
         assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("fdtype", ["forward", "central"])
+def test_cuda_graph_replay(pkg, oracle, dev, fdtype):
+    # use_graph: the call is captured once and replayed; results stay bit-identical, counters advance per replay,
+    # a change of buffers re-captures
+    N = 50000
+    colptr, rowval = tridiag_csc(N)
+    cv = cyc_colors(N, 3)
+    J = pkg.SparseMatrixCSC(N, N, t64(colptr), t64(rowval), torch.full((len(rowval),), float("nan"), dtype=torch.float64, device=dev))
+    ctx = pkg._lib.TridiagCtx(N, 0)
+    f = native(pkg, "fdbs_tridiag", ctx)
+    x = dev_x(pkg, dev, N, 31)
+    cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, use_graph=True)
+    per_call = 4 if fdtype == "forward" else 6
+    for it in range(3):
+        J.nzval.fill_(float("nan"))
+        pkg.finite_difference_jacobian_(J, f, x, cache)
+        torch.cuda.synchronize()
+        ref = np.full(len(rowval), np.nan)
+        oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"),
+                        oracle.fill_x(N, 31), fdtype=FD[fdtype], colorvec=cv, eps_override=cache._last_plan.eps(),
+                        ctx=oracle.SynthTridiagCtx(N, 1))
+        assert np.array_equal(J.nzval.cpu().numpy(), ref)
+        c = cache._last_plan.counters()
+        assert c["jacobians"] == it + 1 and c["f_points"] == per_call * (it + 1)
+    assert ctx.calls == per_call            # the callback itself ran only during the capture
+    # new x buffer with new values -> re-capture, correct result for the new point
+    x2 = dev_x(pkg, dev, N, 32)
+    pkg.finite_difference_jacobian_(J, f, x2, cache)
+    torch.cuda.synchronize()
+    ref = np.full(len(rowval), np.nan)
+    oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"),
+                    oracle.fill_x(N, 32), fdtype=FD[fdtype], colorvec=cv, eps_override=cache._last_plan.eps(),
+                    ctx=oracle.SynthTridiagCtx(N, 1))
+    assert np.array_equal(J.nzval.cpu().numpy(), ref) and ctx.calls == 2 * per_call
+    # in-place update of the SAME x buffer: the replay picks up the new values (eps is recomputed on the device)
+    x2.copy_(x)
+    pkg.finite_difference_jacobian_(J, f, x2, cache)
+    torch.cuda.synchronize()
+    oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"),
+                    oracle.fill_x(N, 31), fdtype=FD[fdtype], colorvec=cv, eps_override=cache._last_plan.eps(),
+                    ctx=oracle.SynthTridiagCtx(N, 1))
+    assert np.array_equal(J.nzval.cpu().numpy(), ref) and ctx.calls == 2 * per_call
+
+
 def test_c2_full_size_bitexact(pkg, oracle, dev):
     """BASELINE config C2 at full size: N=10^7 tridiagonal, 3 colours, forward and central, CSC J — bit-compared
     with the CPU oracle, plus the size-independent property that the Jacobian of the linear stencil is the stencil."""
@@ -400,7 +444,9 @@ def test_lap5_csc_and_banded_bitexact(pkg, oracle, dev, fdtype):
 
 def test_narrow_band_and_rectangular_band(pkg, oracle, dev):
     # narrow-band tiling branch (w=3), non-square m != n, unequal l/u
-    for (m, n, l, u) in [(30, 30, 1, 1), (50, 40, 3, 0), (40, 50, 0, 2), (17, 17, 16, 16)]:
+    # (the last three take the warp-per-column wide-band kernel, l+u+1 >= 64)
+    for (m, n, l, u) in [(30, 30, 1, 1), (50, 40, 3, 0), (40, 50, 0, 2), (17, 17, 16, 16), (300, 200, 70, 10),
+                         (200, 300, 5, 90), (130, 130, 129, 129)]:
         cv = cyc_colors(n, l + u + 1)
         x = dev_x(pkg, dev, n, 77)
         xh = oracle.fill_x(n, 77)
