@@ -203,6 +203,9 @@ def reference_arm(args):
         run()
     dt = time.perf_counter() - t0
     value = nnz * args.steps / dt
+    # the reference itself is single-threaded Julia: also report the port run the way the reference actually runs
+    run1, _, _, _ = cpu_jacobian_runner(args.workload, args.fdtype, 1, scale)
+    med1, reps1 = time_cpu(run1, budget_s=6.0, max_reps=3)
     line = {
         "impl": "reference", "metric": "jacobian_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -213,6 +216,8 @@ def reference_arm(args):
                          "sample": f"{desc}; OpenMP over the reference's full-length passes ({cores} threads; the reference itself is single-threaded)"},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "single_thread": {"value": nnz / med1, "unit": "nnz/s", "cores": 1, "reps": reps1,
+                          "note": "the reference's own execution model (serial broadcast loops)"},
     }
     print(json.dumps(line))
 
@@ -330,7 +335,7 @@ def gpu_arm(args):
     sharded = None
     if world > 1:
         from finitediff_jl_b200 import distributed as fdist
-        sharded = fdist.ShardedJacobian(J, cache, x.numel(), dev)
+        sharded = fdist.ShardedJacobian(J, cache, x.numel(), dev, gather=args.gather)
 
     def step():
         if sharded is not None:
@@ -460,7 +465,7 @@ def gpu_arm(args):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(workload, fdtype), "cuda_graph": bool(args.graph), "l2": "inputs larger than L2 (no flush needed): x, the stacked "
                        "f! outputs and nzval total far more than 126 MB per step" if workload != "c1" else "C1 is L2-resident (latency config)",
-                       "max_batch": args.max_batch, "colors_local": info["n_local_colors"], "scatter_groups": info["n_groups"]},
+                       "max_batch": args.max_batch, "gather": args.gather if world > 1 else None, "colors_local": info["n_local_colors"], "scatter_groups": info["n_groups"]},
             "f_evals_per_s": f_points_all / (ms_total * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "gpu_launches_detail": {"library_kernels": int(lib_launches), "f_callback_invocations": int(f_invocations)},
@@ -483,6 +488,8 @@ def main():
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch eagerly instead of replaying the captured CUDA graph of the call")
+    ap.add_argument("--gather", default="root", choices=["all", "root"],
+                    help="N>1: every rank ends with the full Jacobian (all) or only rank 0 (root)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scale", type=float, default=None, dest="cpu_scale",

@@ -113,6 +113,9 @@ struct fdb_plan {
   // column lists launched right after the colour's f! (random patterns: the slab is gathered from L2; multi-GPU)
   int strategy = 0;
   bool strategy_auto = true;
+  bool double_buffer = false;          // two output buffers so a group's scatter overlaps the next group's f!
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_scat[2] = {nullptr, nullptr};
   int32_t *colptr32 = nullptr, *cols_by_color = nullptr;
   std::vector<int64_t> bucket_start;   // [C+2] offsets into cols_by_color; bucket C = columns without a valid colour
   int lanes = 1;
@@ -324,11 +327,20 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   int64_t pbatch = std::max<int64_t>(batch, std::min<int64_t>(kPerturbMaxPoints, std::max<int64_t>(n_local, 1)));
   while (pbatch > batch && pbatch * 8 * P->ldx * (central ? 2 : 1) > budget / 8) --pbatch;
   P->pbatch = pbatch;
+  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && P->world > 1;
+  const size_t nbuf = P->double_buffer ? 2 : 1;
+  if (P->double_buffer) {
+    CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CU(cudaEventCreateWithFlags(&P->ev_f[b], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&P->ev_scat[b], cudaEventDisableTiming));
+    }
+  }
   TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
-  TRY(P->alloc_t(&P->Fp, (size_t)slabs * P->ldF));
+  TRY(P->alloc_t(&P->Fp, nbuf * (size_t)slabs * P->ldF));
   TRY(P->alloc_t(&P->xp, (size_t)pbatch * P->ldx));
   if (central) {
-    TRY(P->alloc_t(&P->Fm, (size_t)slabs * P->ldF));
+    TRY(P->alloc_t(&P->Fm, nbuf * (size_t)slabs * P->ldF));
     TRY(P->alloc_t(&P->xm, (size_t)pbatch * P->ldx));
   }
   return FDB_OK;
@@ -378,6 +390,8 @@ static void free_plan(fdb_plan *P) {
   for (auto &ev : P->ev_pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto &ev : P->ev_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   if (P->hstream) cudaStreamDestroy(P->hstream);
+  if (P->side) cudaStreamDestroy(P->side);
+  for (int b = 0; b < 2; ++b) { if (P->ev_f[b]) cudaEventDestroy(P->ev_f[b]); if (P->ev_scat[b]) cudaEventDestroy(P->ev_scat[b]); }
   if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
   if (P->cstream) cudaStreamDestroy(P->cstream);
   delete P;
@@ -923,6 +937,12 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   };
 
   // per-colour column-list scatter of local colours [l0, l0+G): <= kMaxSegs colours per launch
+  // Double-buffered overlap (multi-GPU, column lists): group g's f! outputs live in buffer (g & 1); its scatter — the
+  // kernel that also pushes the values to the peers over NVLink — runs on a side stream while the main stream already
+  // evaluates group g+1 into the other buffer.  Events order buffer reuse; everything joins the caller's stream at the end.
+  const bool overlap = P->double_buffer && P->n_peers > 0 && P->side != nullptr;
+  const double *Fp_g = P->Fp, *Fm_g = P->Fm;
+  cudaStream_t ss = s;
   auto scatter_lists = [&](int64_t g, int64_t l0, int64_t G) -> fdb_status {
     const bool zero_bucket = g == 0 && P->rank == 0 && P->bucket_start[(size_t)P->C + 1] > P->bucket_start[(size_t)P->C];
     int64_t li = l0;
@@ -930,7 +950,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     while (li < l0 + G || !zero_done) {
       ColScatterArgs a{};
       a.cols = P->cols_by_color; a.colptr32 = P->colptr32; a.row = P->row32; a.dest = P->dest;
-      a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
+      a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
       a.ldF = P->ldF;
       int ns = 0;
       a.seg_cum[0] = 0;
@@ -951,12 +971,12 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.n_segs = ns;
       const int64_t total = a.seg_cum[ns];
       if (total == 0) continue;
-      ScatterTimer tm(P, s);
+      ScatterTimer tm(P, ss);
       auto go = [&](auto lanes_tag) {
         constexpr int LANES = decltype(lanes_tag)::value;
         const int64_t blocks = (total + (kThreads / LANES) - 1) / (kThreads / LANES);
         const int grid = resident_grid(P, diff_scatter_cols<CENTRAL, LANES>, 0, blocks);
-        diff_scatter_cols<CENTRAL, LANES><<<grid, kThreads, 0, s>>>(a);
+        diff_scatter_cols<CENTRAL, LANES><<<grid, kThreads, 0, ss>>>(a);
       };
       switch (P->lanes) {
         case 1: go(std::integral_constant<int, 1>{}); break;
@@ -1040,10 +1060,29 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     if (li % P->pbatch == 0) TRY(perturb_window(li, std::min<int64_t>(P->pbatch, n_local - li)));
     const int64_t wend = std::min<int64_t>((li / P->pbatch + 1) * P->pbatch, n_local);
     const int64_t fc = std::min<int64_t>(P->batch, std::min<int64_t>(wend - li, gend - li));
-    TRY(call_f(P, f, ctx, P->Fp + (li - g0) * P->ldF, P->xp + (li % P->pbatch) * P->ldx, fc, s));
-    if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + (li - g0) * P->ldF, P->xm + (li % P->pbatch) * P->ldx, fc, s));
+    const int64_t gb = overlap ? (g & 1) * P->slabs * P->ldF : 0;       // this group's output buffer
+    if (overlap && li == g0 && g >= 2) CU(cudaStreamWaitEvent(s, P->ev_scat[g & 1], 0));   // buffer free again?
+    TRY(call_f(P, f, ctx, P->Fp + gb + (li - g0) * P->ldF, P->xp + (li % P->pbatch) * P->ldx, fc, s));
+    if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + gb + (li - g0) * P->ldF, P->xm + (li % P->pbatch) * P->ldx, fc, s));
     li += fc;
-    if (li == gend) TRY(scatter_group(g, g0, gend - g0));
+    if (li == gend) {
+      Fp_g = P->Fp + gb;
+      Fm_g = CENTRAL ? P->Fm + gb : nullptr;
+      if (overlap) {
+        CU(cudaEventRecord(P->ev_f[g & 1], s));
+        CU(cudaStreamWaitEvent(P->side, P->ev_f[g & 1], 0));
+        ss = P->side;
+        TRY(scatter_group(g, g0, gend - g0));
+        CU(cudaEventRecord(P->ev_scat[g & 1], P->side));
+        ss = s;
+      } else {
+        TRY(scatter_group(g, g0, gend - g0));
+      }
+    }
+  }
+  if (overlap) {   // join the side stream back into the caller's stream
+    const int64_t ng = (n_local + P->slabs - 1) / P->slabs;
+    for (int64_t b = 0; b < std::min<int64_t>(ng, 2); ++b) CU(cudaStreamWaitEvent(s, P->ev_scat[b], 0));
   }
   // columns without a valid colour when this rank evaluates no colour at all
   if (n_local == 0 && P->sp_kind == SP_CSC && P->strategy == 1 && P->n_peers > 0) TRY(scatter_group(0, 0, 0));

@@ -117,7 +117,12 @@ class ShardedJacobian:
     group (the cache must have been built with rank=, world=).  After run() every rank holds the complete J."""
 
     def __init__(self, J: api.SparseMatrixCSC, cache: api.JacobianCache, n: int, device, mode: str = "p2p", group=None,
-                 pre_sync: bool = True):
+                 pre_sync: bool = True, gather: str = "all"):
+        """gather="all": every rank ends with the complete J (each value is stored to all peers);
+        gather="root": only rank 0 does (each rank stores its values to rank 0 only: 1/(world-1) of the NVLink traffic)."""
+        if gather not in ("all", "root"):
+            raise ValueError("gather must be 'all' or 'root'")
+        self.gather = gather
         if not isinstance(J, api.SparseMatrixCSC):
             raise TypeError("ShardedJacobian shards CSC Jacobians (dense plans shard columns: Plan.dense_range())")
         self.J, self.cache, self.n, self.device, self.group = J, cache, n, torch.device(device), group
@@ -150,7 +155,7 @@ class ShardedJacobian:
         ptrs = []
         with torch.cuda.device(self.device):
             for r, h in enumerate(handles):
-                if r == self.rank:
+                if r == self.rank or (self.gather == "root" and (r != 0 or self.rank == 0)):
                     continue
                 p = C.c_void_p()
                 L.check(L.lib().fdb_ipc_open(h, C.byref(p)))

@@ -61,14 +61,16 @@ def _worker(rank, world, port, out_dir):
         octx = orc.SynthEllCtx(n, K, colsT.ctypes.data_as(C.POINTER(C.c_int32)), coefT.ctypes.data_as(C.POINTER(C.c_double)), 1)
         for fdtype in ("forward", "central"):
             for mode in ("p2p", "nccl"):
-                for partition in (0, 1):
+                for partition, gather in ((0, "all"), (1, "all"), (0, "root")):
+                    if gather == "root" and mode != "p2p":
+                        continue
                     x = torch.from_numpy(xh).to(dev)
                     J = pkg.SparseMatrixCSC(n, n, torch.from_numpy(colptr), torch.from_numpy(rowval),
                                             torch.full((A.nnz,), float("nan"), dtype=torch.float64, device=dev))
                     ctx = L.EllCtx(n, K, d_cols.data_ptr(), d_coef.data_ptr(), 0)
                     f = pkg.NativeFn(C.cast(L.synth().fdbs_ellrows, C.c_void_p).value, ctx)
                     cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, rank=rank, world=world, partition=partition)
-                    sh = fdist.ShardedJacobian(J, cache, n, dev, mode=mode)
+                    sh = fdist.ShardedJacobian(J, cache, n, dev, mode=mode, gather=gather)
                     assert sh.mode == mode, getattr(sh, "_fallback_reason", "")
                     for _ in range(2):
                         sh.run(f, x)
@@ -84,7 +86,11 @@ def _worker(rank, world, port, out_dir):
                     orc.jacobian(orc.Problem.csc_same(n, n, colptr, rowval), ref, orc.native_fn("synth_ellrows"), xh.copy(),
                                  fdtype=0 if fdtype == "forward" else 1, colorvec=cv, eps_override=eps, ctx=octx)
                     got = J.nzval.cpu().numpy()
-                    assert np.array_equal(got, ref), f"rank {rank} {fdtype} {mode} partition={partition}"
+                    if gather == "all" or rank == 0:
+                        assert np.array_equal(got, ref), f"rank {rank} {fdtype} {mode} partition={partition} {gather}"
+                    else:   # gather="root": a non-root rank holds (at least) its own entries
+                        own = plan.color_owner()[ec] == rank
+                        assert np.array_equal(got[own], ref[own])
                     per_call = ctx.calls // 2
                     assert per_call == (info["n_local_colors"] + 1 if fdtype == "forward" else 2 * info["n_local_colors"])
                     sh.close()
