@@ -348,6 +348,9 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi samples every 100 ms while a timed region can be a few ms: sample across the whole measurement phase
+    # (warm-up, timed region, kernel-timing pass) — all of it is the same kernel sequence under load
+    clocks = Clocks(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -355,7 +358,6 @@ def gpu_arm(args):
     info = plan.info()
     nnz = prob["nnz"] if prob["nnz"] is not None else info["n_entries"]
     c0 = plan.counters()
-    clocks = Clocks(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -368,7 +370,6 @@ def gpu_arm(args):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    clk = clocks.stop() if clocks else None
     c1 = plan.counters()
     f_points = c1["f_points"] - c0["f_points"]
     # the dominant kernel, timed live with CUDA events recorded by the library around its launch (eager launches:
@@ -381,6 +382,7 @@ def gpu_arm(args):
     barrier()
     scat_ms, scat_n = plan.read_timing()
     plan.enable_timing(False)
+    clk = clocks.stop() if clocks else None
     f_launch_per_point = {"c5": 2}.get(workload, 1)
     lib_launches = c1["kernel_launches"] - c0["kernel_launches"]
     f_invocations = c1["f_invocations"] - c0["f_invocations"]
@@ -480,8 +482,8 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: per workload, a few seconds in total)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--fdtype", default="forward", choices=["forward", "central"])
@@ -500,6 +502,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
         args.workload = "c2" if max(args.gpus, world) == 1 else "c4"
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else {"c1": 500, "c2": 200, "c3": 50, "c4": 30, "c5": 5}[args.workload]
     if args.traffic_bytes is None:
         args.traffic_bytes = known_traffic(args.workload, args.fdtype)
     if args.impl == "reference":

@@ -274,7 +274,7 @@ struct BandArgs {
 // shared-memory tables, amortised over the whole column (r1: the per-1024-slot tile version spent most of its time in
 // that dependent-load prologue: 8.1 ms for C3; see profiles/).
 template <typename CT, bool CENTRAL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 diff_scatter_band_wide(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   double *s_eps = reinterpret_cast<double *>(smem);
@@ -313,21 +313,24 @@ diff_scatter_band_wide(const BandArgs a) {
     const double denom = CENTRAL ? 2 * e : e;
     const double *__restrict__ hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF + (c - a.u);
     const double *__restrict__ lo = (CENTRAL ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx) + (c - a.u);
-    // in-matrix slots: rows r = c-u+d in [0, m)  <=>  d in [d_lo, d_hi)
-    const int64_t d_lo = a.u - c > 0 ? a.u - c : 0;
-    const int64_t d_hi = a.m - c + a.u < w ? a.m - c + a.u : w;
+    // in-matrix slots: rows r = c-u+d in [0, m)  <=>  d in [d_lo, d_hi); the corner slots outside the matrix get 0
+    const int64_t d_lo64 = a.u - c > 0 ? a.u - c : 0;
+    const int64_t d_hi64 = a.m - c + a.u < w ? a.m - c + a.u : w;
+    const int wi = (int)w, d_lo = (int)d_lo64, d_hi = (int)(d_hi64 > d_lo64 ? d_hi64 : d_lo64);
     if (a.to_dense) {
       double *__restrict__ out = a.J + c * a.ldJ + (c - a.u);
       if (owned)
-        for (int64_t d = d_lo + lane; d < d_hi; d += 32) out[d] = (__ldg(hi + d) - __ldg(lo + d)) / denom;
+        for (int d = d_lo + lane; d < d_hi; d += 32) out[d] = (__ldg(hi + d) - __ldg(lo + d)) / denom;
     } else {
       double *__restrict__ out = a.J + c * w;
-#pragma unroll 4
-      for (int64_t d = lane; d < w; d += 32) {
-        double v = 0.0;                                    // corner slots outside the matrix get 0
-        if (owned && d >= d_lo && d < d_hi) v = (__ldg(hi + d) - __ldg(lo + d)) / denom;
-        st_stream(out + d, v);
+      for (int d = lane; d < d_lo; d += 32) st_stream(out + d, 0.0);
+      if (owned) {
+#pragma unroll 2
+        for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, (__ldg(hi + d) - __ldg(lo + d)) / denom);
+      } else {
+        for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, 0.0);
       }
+      for (int d = d_hi + lane; d < wi; d += 32) st_stream(out + d, 0.0);
     }
   }
 }

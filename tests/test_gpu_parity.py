@@ -130,6 +130,27 @@ def test_per_colour_list_strategy_tridiag(pkg, oracle, dev, fdtype):
 
 
 @pytest.mark.parametrize("fdtype", ["forward", "central"])
+def test_unaligned_buffers_take_scalar_paths(pkg, oracle, dev, fdtype):
+    # x and nzval only 8-byte aligned (views at an odd offset): the 16-byte vector paths must fall back, same bits
+    from _util import f_tridiag
+    N = 5003
+    colptr, rowval = tridiag_csc(N)
+    cv = cyc_colors(N, 3)
+    xbuf = torch.zeros(N + 1, dtype=torch.float64, device=dev)
+    x = xbuf[1:]
+    x.copy_(dev_x(pkg, dev, N, 41))
+    assert x.data_ptr() % 16 == 8
+    nzbuf = torch.full((len(rowval) + 1,), float("nan"), dtype=torch.float64, device=dev)
+    J = pkg.SparseMatrixCSC(N, N, t64(colptr), t64(rowval), nzbuf[1:])
+    cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J)
+    pkg.finite_difference_jacobian_(J, f_tridiag_t, x, cache)
+    ref = np.full(len(rowval), np.nan)
+    oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, f_tridiag, oracle.fill_x(N, 41), fdtype=FD[fdtype],
+                    colorvec=cv, eps_override=cache._last_plan.eps())
+    assert np.array_equal(J.nzval.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("fdtype", ["forward", "central"])
 def test_cuda_graph_replay(pkg, oracle, dev, fdtype):
     # use_graph: the call is captured once and replayed; results stay bit-identical, counters advance per replay,
     # a change of buffers re-captures
