@@ -135,6 +135,25 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def usable_cores() -> int:
+    """Host threads this process can really use: scheduler affinity capped by the cgroup CPU quota (the GPU boxes report
+    128 CPUs but run the container under a 16-CPU quota: 128 OpenMP threads there are ~300x SLOWER than 16)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        try:
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            p = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def cpu_jacobian_runner(workload, fdtype, nthreads, scale=1.0):
     """Returns (run_once, nnz, n_fcalls, description) for the oracle on `workload` (bounded size: scale<1 shrinks n)."""
     from oracle import fd_oracle as orc
@@ -193,7 +212,7 @@ def reference_arm(args):
         return
     from oracle import fd_oracle as orc
     orc.build()
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     scale = args.cpu_scale
     run, nnz, fcalls, desc = cpu_jacobian_runner(args.workload, args.fdtype, cores, scale)
     for _ in range(args.warmup):
@@ -457,7 +476,7 @@ def gpu_arm(args):
         run, cnnz, cf, desc = cpu_jacobian_runner(workload, fdtype, 1, scale)
         med, reps = time_cpu(run, budget_s=14.0, max_reps=5)
         cpu = {"value": cnnz / med, "unit": "nnz/s", "cores": 1, "kind": "port",
-               "sample": f"{reps} full Jacobian(s) of {desc} (median {med:.3f} s); host has {os.cpu_count()} cores",
+               "sample": f"{reps} full Jacobian(s) of {desc} (median {med:.3f} s); host offers {usable_cores()} usable cores",
                "f_evals_per_s": cf / med}
 
     if rank == 0:
@@ -490,8 +509,9 @@ def main():
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch eagerly instead of replaying the captured CUDA graph of the call")
-    ap.add_argument("--gather", default="root", choices=["all", "root"],
-                    help="N>1: every rank ends with the full Jacobian (all) or only rank 0 (root)")
+    ap.add_argument("--gather", default="root", choices=["all", "root", "all_p2p"],
+                    help="N>1: rank 0 ends with the full Jacobian (root: fused NVLink gather), or every rank does "
+                         "(all: root gather + NCCL broadcast; all_p2p: every value stored to every peer)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scale", type=float, default=None, dest="cpu_scale",

@@ -4,9 +4,11 @@ Colours are independent units given x (each colour = perturb -> f! -> diff -> sc
 so there is NO collective on the data path until the end, where every rank needs the entries the others computed.
 Two implementations of that final exchange:
 
-  "p2p"  (default on NVLink/NVSwitch)  the diff+scatter kernel itself stores every value it owns into EVERY rank's
-         nzval buffer (peer pointers from CUDA IPC, passed to the plan with fdb_plan_set_peers) — compute and gather
-         are one kernel; a stream-ordered NCCL all-reduce of one flag word is the only barrier.
+  "p2p"  (default on NVLink/NVSwitch)  the diff+scatter kernel itself stores every value it owns into rank 0's nzval
+         buffer (gather="root"; peer pointer from CUDA IPC, passed to the plan with fdb_plan_set_peers) — compute and
+         gather are one kernel, overlapped with the next colour's f! on a side stream; a stream-ordered NCCL all-reduce
+         of one flag word is the only barrier.  gather="all" adds one NCCL broadcast of nzval; gather="all_p2p" stores
+         to every peer from the kernel (fine up to 4 GPUs, pathological at 8 — see ShardedJacobian).
   "nccl" (fallback; also what the CPU/gloo tests exercise)  each rank packs the entries it owns into a compact
          buffer, all_gather, then un-permutes into nzval.
 
@@ -118,10 +120,14 @@ class ShardedJacobian:
 
     def __init__(self, J: api.SparseMatrixCSC, cache: api.JacobianCache, n: int, device, mode: str = "p2p", group=None,
                  pre_sync: bool = True, gather: str = "all"):
-        """gather="all": every rank ends with the complete J (each value is stored to all peers);
-        gather="root": only rank 0 does (each rank stores its values to rank 0 only: 1/(world-1) of the NVLink traffic)."""
-        if gather not in ("all", "root"):
-            raise ValueError("gather must be 'all' or 'root'")
+        """gather="root": rank 0 ends with the complete J — every rank's scatter kernel stores its values straight into
+        rank 0's nzval (the literal "final gather of Jacobian columns");
+        gather="all": every rank does: the same fused gather to rank 0, then one NCCL broadcast of nzval (bulk, full
+        NVLink bandwidth);
+        gather="all_p2p": every value is stored to EVERY peer by the scatter kernel.  Fine up to 4 GPUs (3.35x at 4), but
+        measured 16 ms at 8 GPUs (7 peer apertures x scattered 64-byte runs) — kept for experiments only."""
+        if gather not in ("all", "root", "all_p2p"):
+            raise ValueError("gather must be 'all', 'root' or 'all_p2p'")
         self.gather = gather
         if not isinstance(J, api.SparseMatrixCSC):
             raise TypeError("ShardedJacobian shards CSC Jacobians (dense plans shard columns: Plan.dense_range())")
@@ -155,7 +161,7 @@ class ShardedJacobian:
         ptrs = []
         with torch.cuda.device(self.device):
             for r, h in enumerate(handles):
-                if r == self.rank or (self.gather == "root" and (r != 0 or self.rank == 0)):
+                if r == self.rank or (self.gather != "all_p2p" and (r != 0 or self.rank == 0)):
                     continue
                 p = C.c_void_p()
                 L.check(L.lib().fdb_ipc_open(h, C.byref(p)))
@@ -171,6 +177,8 @@ class ShardedJacobian:
         api.finite_difference_jacobian_(self.J, f, x, self.cache, **kw)
         if self.mode == "p2p":
             dist.all_reduce(self.flag, group=self.group)    # every rank's scatter (incl. its peer stores) has completed
+            if self.gather == "all":
+                dist.broadcast(self.J.nzval, src=0, group=self.group)
         else:
             allgather_owned(self.J.nzval, self.gp, self.rank, self.group)
         return None

@@ -61,8 +61,8 @@ def _worker(rank, world, port, out_dir):
         octx = orc.SynthEllCtx(n, K, colsT.ctypes.data_as(C.POINTER(C.c_int32)), coefT.ctypes.data_as(C.POINTER(C.c_double)), 1)
         for fdtype in ("forward", "central"):
             for mode in ("p2p", "nccl"):
-                for partition, gather in ((0, "all"), (1, "all"), (0, "root")):
-                    if gather == "root" and mode != "p2p":
+                for partition, gather in ((0, "all"), (1, "all"), (0, "root"), (1, "all_p2p")):
+                    if gather != "all" and mode != "p2p":
                         continue
                     x = torch.from_numpy(xh).to(dev)
                     J = pkg.SparseMatrixCSC(n, n, torch.from_numpy(colptr), torch.from_numpy(rowval),
@@ -86,7 +86,7 @@ def _worker(rank, world, port, out_dir):
                     orc.jacobian(orc.Problem.csc_same(n, n, colptr, rowval), ref, orc.native_fn("synth_ellrows"), xh.copy(),
                                  fdtype=0 if fdtype == "forward" else 1, colorvec=cv, eps_override=eps, ctx=octx)
                     got = J.nzval.cpu().numpy()
-                    if gather == "all" or rank == 0:
+                    if gather != "root" or rank == 0:
                         assert np.array_equal(got, ref), f"rank {rank} {fdtype} {mode} partition={partition} {gather}"
                     else:   # gather="root": a non-root rank holds (at least) its own entries
                         own = plan.color_owner()[ec] == rank
