@@ -14,7 +14,7 @@ LIB_PATH = HERE / "libfdjac_b200.so"
 SYNTH_PATH = HERE / "libfdjac_synth.so"
 
 FDB_OK, FDB_ERR_INVALID, FDB_ERR_CUDA, FDB_ERR_CALLBACK, FDB_ERR_NOMEM, FDB_ERR_UNSUPPORTED, FDB_ERR_NO_DEVICE = range(7)
-FDB_FORWARD, FDB_CENTRAL = 0, 1
+FDB_FORWARD, FDB_CENTRAL, FDB_COMPLEX = 0, 1, 2
 FDB_J_CSC_NZVAL, FDB_J_DENSE, FDB_J_BAND, FDB_J_SLOTS = 0, 1, 2, 3
 
 # int (*fdb_fn)(void* ctx, double* d_fx, const double* d_x, int64 batch, int64 ldfx, int64 ldx, void* stream)
@@ -74,6 +74,7 @@ ABI_SYMBOLS = {
     "fdb_plan_enable_timing": (_int, [_vp, _int]),
     "fdb_plan_read_timing": (_int, [_vp, C.POINTER(_f64), C.POINTER(_i64)]),
     "fdb_jacobian": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
+    "fdb_jacobian_complex": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "fdb_jacobian_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64]),
     "fdb_host_alloc": (_int, [_PP, C.c_size_t]),
     "fdb_host_free": (_int, [_vp]),
@@ -89,6 +90,7 @@ ABI_SYMBOLS = {
 
 SYNTH_SYMBOLS = {
     "fdbs_tridiag": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "fdbs_tridiag_c": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_lap5": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_ellrows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_rank1": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),

@@ -35,17 +35,16 @@ __all__ = [
 
 _DEFAULT = object()
 
-_FDTYPES = {"forward": L.FDB_FORWARD, "central": L.FDB_CENTRAL, L.FDB_FORWARD: L.FDB_FORWARD,
-            L.FDB_CENTRAL: L.FDB_CENTRAL}
+_FDTYPES = {"forward": L.FDB_FORWARD, "central": L.FDB_CENTRAL, "complex": L.FDB_COMPLEX, L.FDB_FORWARD: L.FDB_FORWARD,
+            L.FDB_CENTRAL: L.FDB_CENTRAL, L.FDB_COMPLEX: L.FDB_COMPLEX}
 
 
 def _fdtype_code(fdtype) -> int:
     if isinstance(fdtype, str):
         fdtype = fdtype.lstrip(":")
     if fdtype not in _FDTYPES:
-        # epsilons.jl:159-167 fdtype_error (":complex" is §8f "next", not built)
-        raise ValueError("Unrecognized fdtype: valid values are 'forward' and 'central' "
-                         "(complex-step is not implemented by the B200 path).")
+        # epsilons.jl:159-167 fdtype_error
+        raise ValueError("Unrecognized fdtype: valid values are 'forward', 'central' and 'complex'.")
     return _FDTYPES[fdtype]
 
 
@@ -110,8 +109,8 @@ def pinned_empty(count: int) -> np.ndarray:
 class _DevArray:
     """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v3)."""
 
-    def __init__(self, ptr: int, shape, strides=None):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr: int, shape, strides=None, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 3, "strides": strides}
 
 
@@ -247,10 +246,12 @@ class _PyFn:
     """Wraps a Python f!(fx, x) working on CUDA tensors as an fdb_fn.  `batched=True` callables receive 2-D
     (batch, m) / (batch, n) tensors; otherwise they are called once per point with 1-D tensors."""
 
-    def __init__(self, f: Callable, m: int, n: int, device: torch.device, batched: bool):
+    def __init__(self, f: Callable, m: int, n: int, device: torch.device, batched: bool, complex_: bool = False):
         self.f, self.m, self.n, self.device, self.batched = f, m, n, device, batched
         self.exc: Optional[BaseException] = None
         self.calls = 0
+        # complex-step callbacks (fdb_fn_c) see complex128 tensors; ld* then count complex elements
+        self.typestr, self.esize = ("<c16", 16) if complex_ else ("<f8", 8)
         self.cfunc = L.FDB_FN(self._tramp)
 
     def _tramp(self, _ctx, p_fx, p_x, batch, ldfx, ldx, stream):
@@ -261,8 +262,9 @@ class _PyFn:
                 ctx = torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=self.device))
                 ctx.__enter__()
             try:
-                fx2 = torch.as_tensor(_DevArray(p_fx, (batch, self.m), (ldfx * 8, 8)), device=self.device)
-                x2 = torch.as_tensor(_DevArray(p_x, (batch, self.n), (ldx * 8, 8)), device=self.device)
+                es = self.esize
+                fx2 = torch.as_tensor(_DevArray(p_fx, (batch, self.m), (ldfx * es, es), self.typestr), device=self.device)
+                x2 = torch.as_tensor(_DevArray(p_x, (batch, self.n), (ldx * es, es), self.typestr), device=self.device)
                 if self.batched:
                     self.calls += int(batch)
                     self.f(fx2, x2)
@@ -504,7 +506,13 @@ class JacobianCache:
             raise TypeError("only Float64 is supported by the B200 path")
         if not _is_cuda(x1):
             raise TypeError("JacobianCache needs CUDA float64 tensors (this path has no CPU implementation)")
-        if fx is None and fx1 is None:
+        if _fdtype_code(self.fdtype) == L.FDB_COMPLEX:
+            # complex step: x1 and fx are complex (`false .* im .* x`), fx1 === nothing  (:20-32, :60-76, :105-117)
+            fx_like = x1 if fx is None else fx
+            self.x1 = torch.zeros(x1.shape, dtype=torch.complex128, device=x1.device)
+            self.fx = torch.zeros(fx_like.shape, dtype=torch.complex128, device=x1.device)
+            self.fx1 = None
+        elif fx is None and fx1 is None:
             self.x1, self.fx, self.fx1 = x1.clone(), x1.clone(), x1.clone()           # :25-33
         elif fx1 is None:
             self.x1, self.fx, self.fx1 = x1.clone(), fx.clone(), fx.clone()           # :62-76
@@ -556,10 +564,10 @@ def resize_(cache: JacobianCache, i: int):
 
 
 # ------------------------------------------------------------------------------------------------ the public call
-def _as_fn(f, m, n, device, plan_batch):
+def _as_fn(f, m, n, device, plan_batch, complex_=False):
     if isinstance(f, NativeFn):
         return f.address, f.ctx_ptr, None
-    w = _PyFn(f, m, n, device, bool(getattr(f, "batched", False)))
+    w = _PyFn(f, m, n, device, bool(getattr(f, "batched", False)), complex_)
     return L.fn_address(w.cfunc), None, w
 
 
@@ -620,9 +628,19 @@ def finite_difference_jacobian_(J, f, x, cache=None, f_in=None, returntype=None,
         raise TypeError("J's value storage must be a float64 CUDA tensor")
     if cache.fx.numel() != m:
         raise ValueError(f"length(cache.fx)={cache.fx.numel()} != size(J,1)={m} (use the 3-array constructor)")
-    addr, ctx, pyfn = _as_fn(f, m, n, x.device, 1)
+    addr, ctx, pyfn = _as_fn(f, m, n, x.device, 1, fd == L.FDB_COMPLEX)
     if stream is None:
         stream = torch.cuda.current_stream(x.device).cuda_stream
+    if fd == L.FDB_COMPLEX:
+        # jacobians.jl:623-648: one complex evaluation per colour, J = imag(f(x + im*eps*e_k))/eps, eps = eps(Float64)
+        with torch.cuda.device(x.device):
+            st = L.lib().fdb_jacobian_complex(plan.handle, addr, ctx, xv.data_ptr(), jv.data_ptr(), C.c_void_p(stream))
+        if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
+            exc, pyfn.exc = pyfn.exc, None
+            raise exc
+        L.check(st)
+        cache._last_plan = plan
+        return None
     fin_ptr = None
     if f_in is not None and fd == L.FDB_FORWARD:
         f_in = f_in.reshape(-1)

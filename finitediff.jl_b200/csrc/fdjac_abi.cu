@@ -135,6 +135,7 @@ struct fdb_plan {
   fdb_counters_t cnt{};
   int64_t alg_bytes = 0;
   int64_t last_eps_count = 0;
+  bool complex_entry = false;   // set while fdb_jacobian_complex drives the call
   // optional CUDA-graph replay of the whole call
   bool use_graph = false;
   cudaStream_t cstream = nullptr;
@@ -303,12 +304,13 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
 
   // scratch: stacked f! outputs (slabs) + perturbed points
   const bool central = P->fdtype == FDB_CENTRAL;
+  const int64_t cw = P->fdtype == FDB_COMPLEX ? 2 : 1;     // doubles per element of the f! in/outputs
   P->ldF = (P->m + 1) & ~(int64_t)1;
   P->ldx = (P->n + 1) & ~(int64_t)1;
   if (P->ldF < 2) P->ldF = 2;
   if (P->ldx < 2) P->ldx = 2;
   int64_t budget = (o && o->scratch_bytes > 0) ? o->scratch_bytes : (int64_t)8 << 30;
-  const int64_t per_slab = 8 * P->ldF * (central ? 2 : 1);
+  const int64_t per_slab = 8 * cw * P->ldF * (central ? 2 : 1);
   int64_t slabs = std::max<int64_t>(1, budget / per_slab);
   slabs = std::min<int64_t>(slabs, std::max<int64_t>(n_local, 1));
   if (P->sp_kind == SP_CSC && P->strategy == 0 && P->strategy_auto && slabs < n_local) P->strategy = 1;
@@ -325,7 +327,7 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   // even when f! takes one point per call, build up to kPerturbMaxPoints points per pass over x (one read of x and
   // the colour stream instead of one per colour) when the point buffers fit in an eighth of the scratch budget
   int64_t pbatch = std::max<int64_t>(batch, std::min<int64_t>(kPerturbMaxPoints, std::max<int64_t>(n_local, 1)));
-  while (pbatch > batch && pbatch * 8 * P->ldx * (central ? 2 : 1) > budget / 8) --pbatch;
+  while (pbatch > batch && pbatch * 8 * cw * P->ldx * (central ? 2 : 1) > budget / 8) --pbatch;
   P->pbatch = pbatch;
   P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && P->world > 1;
   const size_t nbuf = P->double_buffer ? 2 : 1;
@@ -337,8 +339,8 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
     }
   }
   TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
-  TRY(P->alloc_t(&P->Fp, nbuf * (size_t)slabs * P->ldF));
-  TRY(P->alloc_t(&P->xp, (size_t)pbatch * P->ldx));
+  TRY(P->alloc_t(&P->Fp, nbuf * (size_t)slabs * P->ldF * cw));
+  TRY(P->alloc_t(&P->xp, (size_t)pbatch * P->ldx * cw));
   if (central) {
     TRY(P->alloc_t(&P->Fm, nbuf * (size_t)slabs * P->ldF));
     TRY(P->alloc_t(&P->xm, (size_t)pbatch * P->ldx));
@@ -360,8 +362,8 @@ static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, in
   *out = nullptr;
   if (m < 0 || n < 0) return fail(FDB_ERR_INVALID, "negative dimensions m=%lld n=%lld", (long long)m, (long long)n);
   if (m > 0x7FFFFFF0LL || n > 0x7FFFFFF0LL) return fail(FDB_ERR_UNSUPPORTED, "m, n must be < 2^31");
-  if (o && o->fdtype != FDB_FORWARD && o->fdtype != FDB_CENTRAL)
-    return fail(FDB_ERR_UNSUPPORTED, "Unrecognized fdtype: valid values are forward (0) and central (1)");
+  if (o && o->fdtype != FDB_FORWARD && o->fdtype != FDB_CENTRAL && o->fdtype != FDB_COMPLEX)
+    return fail(FDB_ERR_UNSUPPORTED, "Unrecognized fdtype: valid values are forward (0), central (1) and complex (2)");
   int dev = 0;
   TRY(check_device(o, &dev));
   fdb_plan *P = new (std::nothrow) fdb_plan();
@@ -697,7 +699,8 @@ fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t 
   P->ldx = std::max<int64_t>(2, (n + 1) & ~(int64_t)1);
   int64_t batch = (opts && opts->max_batch > 1) ? opts->max_batch : 1;
   int64_t budget = (opts && opts->scratch_bytes > 0) ? opts->scratch_bytes : (int64_t)8 << 30;
-  const int64_t per_point = 8 * (P->ldx + P->ldF * (central ? 2 : 1));
+  const int64_t cw = P->fdtype == FDB_COMPLEX ? 2 : 1;
+  const int64_t per_point = 8 * cw * (P->ldx + P->ldF * (central ? 2 : 1));
   batch = std::max<int64_t>(1, std::min<int64_t>(batch, budget / per_point));
   batch = std::min<int64_t>(batch, std::max<int64_t>(ncl, 1));
   batch = std::min<int64_t>(batch, 65535);   // gridDim.y of diff_columns
@@ -705,9 +708,9 @@ fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t 
   P->slabs = batch;
   P->n_groups = ncl == 0 ? 0 : (ncl + batch - 1) / batch;
   PLAN_TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
-  PLAN_TRY(P->alloc_t(&P->Fp, (size_t)batch * P->ldF));
+  PLAN_TRY(P->alloc_t(&P->Fp, (size_t)batch * P->ldF * cw));
   if (central) PLAN_TRY(P->alloc_t(&P->Fm, (size_t)batch * P->ldF));
-  PLAN_TRY(P->alloc_t(&P->xp, (size_t)batch * P->ldx));
+  PLAN_TRY(P->alloc_t(&P->xp, (size_t)batch * P->ldx * cw));
   PLAN_TRY(P->alloc_t(&P->eps_cols, (size_t)std::max<int64_t>(ncl, 1)));
   // SURVEY.md §8(d) dense: 24*m per column
   P->alg_bytes = 24 * m * ncl;
@@ -731,7 +734,7 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
   info->n_local_colors = n_local;
   info->n_groups = P->n_groups;
   info->slabs = P->slabs;
-  info->fcalls_per_jacobian = P->fdtype == FDB_CENTRAL ? 2 * n_local : 1 + n_local;
+  info->fcalls_per_jacobian = P->fdtype == FDB_CENTRAL ? 2 * n_local : (P->fdtype == FDB_COMPLEX ? n_local : 1 + n_local);
   info->device_bytes = (int64_t)P->device_bytes;
   info->fdtype = P->fdtype;
   info->jkind = P->jkind;
@@ -867,6 +870,12 @@ template <typename CT>
 static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double absstep, double dir, cudaStream_t s) {
   const int32_t C = P->C;
   if (C <= 0) return FDB_OK;
+  if (P->fdtype == FDB_COMPLEX) {   // epsilon = eps(eltype(x))  jacobians.jl:624 — the same for every colour
+    fill_value<<<(C + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->eps, C, DBL_EPSILON);
+    P->cnt.kernel_launches += 1;
+    CU(cudaGetLastError());
+    return FDB_OK;
+  }
   EpsParams prm{P->fdtype == FDB_CENTRAL ? 1 : 0, relstep, absstep, dir};
   if (C <= kEpsRegColors) {
     const int64_t ntiles = (P->n + kTile - 1) / kTile;
@@ -896,9 +905,13 @@ static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double a
   return FDB_OK;
 }
 
-template <typename CT, bool CENTRAL>
+template <typename CT, int MODE>
 static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x, double *J, double *fx,
                               const double *f_in, double relstep, double absstep, double dir, cudaStream_t s) {
+  constexpr bool CENTRAL = MODE == kCentral;
+  constexpr bool COMPLEX = MODE == kComplex;
+  // strides, in doubles, of one f! output slab / one perturbed point (complex128 in complex-step mode)
+  const int64_t sF = COMPLEX ? 2 * P->ldF : P->ldF, sX = COMPLEX ? 2 * P->ldx : P->ldx;
   const int64_t n_local = (int64_t)P->local_colors.size();
   // fill_matrix!(J, false)  jacobians.jl:530-532 — needed where the scatter does not define every slot itself
   const bool ident = P->dest == nullptr && P->sp_kind != SP_BANDED;
@@ -910,7 +923,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   if (!self_defining && P->n_peers == 0 && P->j_len > 0) CU(cudaMemsetAsync(J, 0, (size_t)P->j_len * 8, s));
   TRY(run_eps<CT>(P, x, relstep, absstep, dir, s));
   const double *vfx = nullptr;
-  if (!CENTRAL) {
+  if (MODE == kForward) {
     if (f_in) vfx = f_in;                                  // jacobians.jl:543-544
     else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; } // :541-542
   }
@@ -919,15 +932,18 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       for (int64_t q0 = 0; q0 < kc; q0 += kPerturbMaxPoints) {
         PerturbArgs pa{};
         pa.x = x; pa.jcolor = P->jcolor; pa.eps = P->eps;
-        pa.xp = P->xp + q0 * P->ldx; pa.xm = CENTRAL ? P->xm + q0 * P->ldx : nullptr;
-        pa.n = P->n; pa.ldx = P->ldx; pa.C = P->C; pa.drift = P->no_drift ? 0 : 1;
+        pa.xp = P->xp + q0 * sX; pa.xm = CENTRAL ? P->xm + q0 * sX : nullptr;
+        pa.n = P->n; pa.ldx = sX; pa.C = P->C; pa.drift = P->no_drift ? 0 : 1;
         pa.kcount = (int32_t)std::min<int64_t>(kPerturbMaxPoints, kc - q0);
         for (int32_t q = 0; q < pa.kcount; ++q) pa.k[q] = P->local_colors[(size_t)(li0 + q0 + q)];
         pa.aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(P->xp) |
                        reinterpret_cast<uintptr_t>(P->xm)) & 15) == 0 && (P->ldx & 1) == 0;
         const size_t sm = P->C <= kPerturbSmemColors ? (size_t)P->C * sizeof(double) : 0;
         const int64_t tiles = (P->n + kTile - 1) / kTile;
-        if (pa.kcount == 1)
+        if (COMPLEX) {
+          if (pa.kcount == 1) perturb_complex<CT, 1><<<P->grid(P->n), kThreads, 0, s>>>(pa);
+          else perturb_complex<CT, kPerturbMaxPoints><<<P->grid(P->n), kThreads, 0, s>>>(pa);
+        } else if (pa.kcount == 1)
           perturb_colors<CT, CENTRAL, 1><<<resident_grid(P, perturb_colors<CT, CENTRAL, 1>, sm, tiles), kThreads, sm, s>>>(pa);
         else
           perturb_colors<CT, CENTRAL, kPerturbMaxPoints><<<resident_grid(P, perturb_colors<CT, CENTRAL, kPerturbMaxPoints>, sm, tiles), kThreads, sm, s>>>(pa);
@@ -951,7 +967,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       ColScatterArgs a{};
       a.cols = P->cols_by_color; a.colptr32 = P->colptr32; a.row = P->row32; a.dest = P->dest;
       a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
-      a.ldF = P->ldF;
+      a.ldF = sF;
       int ns = 0;
       a.seg_cum[0] = 0;
       if (!zero_done) {
@@ -975,8 +991,8 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       auto go = [&](auto lanes_tag) {
         constexpr int LANES = decltype(lanes_tag)::value;
         const int64_t blocks = (total + (kThreads / LANES) - 1) / (kThreads / LANES);
-        const int grid = resident_grid(P, diff_scatter_cols<CENTRAL, LANES>, 0, blocks);
-        diff_scatter_cols<CENTRAL, LANES><<<grid, kThreads, 0, ss>>>(a);
+        const int grid = resident_grid(P, diff_scatter_cols<MODE, LANES>, 0, blocks);
+        diff_scatter_cols<MODE, LANES><<<grid, kThreads, 0, ss>>>(a);
       };
       switch (P->lanes) {
         case 1: go(std::integral_constant<int, 1>{}); break;
@@ -1000,23 +1016,23 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.J = J; a.C = P->C; a.l0 = (int32_t)l0; a.G = (int32_t)G;
       a.write_other = (g == 0 && P->rank == 0) ? 1 : 0;
       a.to_dense = P->jkind == FDB_J_DENSE ? 1 : 0;
-      a.ldF = P->ldF; a.ldJ = P->ldJ; a.m = P->m; a.n = P->n; a.l = P->l; a.u = P->u;
+      a.ldF = sF; a.ldJ = P->ldJ; a.m = P->m; a.n = P->n; a.l = P->l; a.u = P->u;
       const int64_t w = P->l + P->u + 1;
       int64_t ntiles;
-      if (w >= 512) { a.chunks_per_col = (w + kThreads * 4 - 1) / (kThreads * 4); a.cols_per_tile = 0; ntiles = P->n * a.chunks_per_col; }
-      else { a.chunks_per_col = 0; a.cols_per_tile = std::max<int64_t>(1, 4096 / w); ntiles = (P->n + a.cols_per_tile - 1) / a.cols_per_tile; }
+      a.cols_per_tile = std::max<int64_t>(1, 4096 / w);
+      ntiles = (P->n + a.cols_per_tile - 1) / a.cols_per_tile;
       if (w >= 64 && P->n > 0) {
         // wide band: one warp per column
         const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
-        const int grid = resident_grid(P, diff_scatter_band_wide<CT, CENTRAL>, sm, (P->n + 7) / 8);
+        const int grid = resident_grid(P, diff_scatter_band_wide<CT, MODE>, sm, (P->n + 7) / 8);
         ScatterTimer tm(P, s);
-        diff_scatter_band_wide<CT, CENTRAL><<<grid, kThreads, sm, s>>>(a);
+        diff_scatter_band_wide<CT, MODE><<<grid, kThreads, sm, s>>>(a);
         P->cnt.kernel_launches += 1;
         P->cnt.scatter_launches += 1;
       } else if (ntiles > 0) {
         const int blocks = (int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16);
         ScatterTimer tm(P, s);
-        diff_scatter_band<CT, CENTRAL><<<blocks, kThreads, 0, s>>>(a);
+        diff_scatter_band<CT, MODE><<<blocks, kThreads, 0, s>>>(a);
         P->cnt.kernel_launches += 1;
         P->cnt.scatter_launches += 1;
       }
@@ -1026,7 +1042,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.local_of = P->local_of; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers; a.C = P->C;
       a.l0 = (int32_t)l0; a.G = (int32_t)G;
       a.write_invalid_zero = (g == 0 && P->rank == 0 && P->has_invalid) ? 1 : 0;
-      a.ldF = P->ldF; a.E = P->E;
+      a.ldF = sF; a.E = P->E;
       a.j_aligned = (reinterpret_cast<uintptr_t>(J) & 15) == 0 && P->peers_aligned;
       const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
       ScatterTimer tm(P, s);
@@ -1035,15 +1051,15 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
         // single group on a single rank: every valid colour is resident -> the FULL variant (no ownership tests)
         const bool full = P->n_groups == 1 && P->world == 1 && P->n_peers == 0;
         if (full) {
-          const int grid = resident_grid(P, diff_scatter_ident<CT, CENTRAL, true, kScatterMinBlocks>, sm, tiles);
-          diff_scatter_ident<CT, CENTRAL, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
+          const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);
+          diff_scatter_ident<CT, MODE, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
         } else {
-          const int grid = resident_grid(P, diff_scatter_ident<CT, CENTRAL, false, kScatterMinBlocks>, sm, tiles);
-          diff_scatter_ident<CT, CENTRAL, false, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
+          const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, false, kScatterMinBlocks>, sm, tiles);
+          diff_scatter_ident<CT, MODE, false, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
         }
       } else {
-        const int grid = resident_grid(P, diff_scatter_dest<CT, CENTRAL>, sm, (P->E + kThreads - 1) / kThreads);
-        diff_scatter_dest<CT, CENTRAL><<<grid, kThreads, sm, s>>>(a);
+        const int grid = resident_grid(P, diff_scatter_dest<CT, MODE>, sm, (P->E + kThreads - 1) / kThreads);
+        diff_scatter_dest<CT, MODE><<<grid, kThreads, sm, s>>>(a);
       }
       P->cnt.kernel_launches += 1;
       P->cnt.scatter_launches += 1;
@@ -1060,10 +1076,10 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     if (li % P->pbatch == 0) TRY(perturb_window(li, std::min<int64_t>(P->pbatch, n_local - li)));
     const int64_t wend = std::min<int64_t>((li / P->pbatch + 1) * P->pbatch, n_local);
     const int64_t fc = std::min<int64_t>(P->batch, std::min<int64_t>(wend - li, gend - li));
-    const int64_t gb = overlap ? (g & 1) * P->slabs * P->ldF : 0;       // this group's output buffer
+    const int64_t gb = overlap ? (g & 1) * P->slabs * sF : 0;           // this group's output buffer
     if (overlap && li == g0 && g >= 2) CU(cudaStreamWaitEvent(s, P->ev_scat[g & 1], 0));   // buffer free again?
-    TRY(call_f(P, f, ctx, P->Fp + gb + (li - g0) * P->ldF, P->xp + (li % P->pbatch) * P->ldx, fc, s));
-    if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + gb + (li - g0) * P->ldF, P->xm + (li % P->pbatch) * P->ldx, fc, s));
+    TRY(call_f(P, f, ctx, P->Fp + gb + (li - g0) * sF, P->xp + (li % P->pbatch) * sX, fc, s));
+    if (CENTRAL) TRY(call_f(P, f, ctx, P->Fm + gb + (li - g0) * sF, P->xm + (li % P->pbatch) * sX, fc, s));
     li += fc;
     if (li == gend) {
       Fp_g = P->Fp + gb;
@@ -1090,20 +1106,29 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   return FDB_OK;
 }
 
-template <bool CENTRAL>
+template <int MODE>
 static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, double *J, double *fx, const double *f_in,
                             double relstep, double absstep, double dir, cudaStream_t s) {
+  constexpr bool CENTRAL = MODE == kCentral;
+  constexpr bool COMPLEX = MODE == kComplex;
+  const int64_t sF = COMPLEX ? 2 * P->ldF : P->ldF, sX = COMPLEX ? 2 * P->ldx : P->ldx;
   const int64_t ncl = P->col_end - P->col_begin;
   const double *vfx = nullptr;
-  if (!CENTRAL) {
+  if (MODE == kForward) {
     if (f_in) vfx = f_in;
     else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; }
   }
   if (ncl == 0) return FDB_OK;
-  component_eps<<<(int)((ncl + kThreads - 1) / kThreads), kThreads, 0, s>>>(x, P->col_begin, ncl, CENTRAL ? 1 : 0, relstep,
-                                                                          absstep, dir, P->eps_cols);
   const int32_t B = (int32_t)P->batch;
-  replicate_x<<<P->grid(P->n), kThreads, 0, s>>>(x, P->n, P->ldx, B, P->xp);
+  if (COMPLEX) {
+    // epsilon = eps(eltype(x)) for every column (jacobians.jl:624); X[b] = complex(x)
+    fill_value<<<(int)((ncl + kThreads - 1) / kThreads), kThreads, 0, s>>>(P->eps_cols, ncl, DBL_EPSILON);
+    replicate_x_complex<<<P->grid(P->n), kThreads, 0, s>>>(x, P->n, sX, B, P->xp);
+  } else {
+    component_eps<<<(int)((ncl + kThreads - 1) / kThreads), kThreads, 0, s>>>(x, P->col_begin, ncl, CENTRAL ? 1 : 0, relstep,
+                                                                            absstep, dir, P->eps_cols);
+    replicate_x<<<P->grid(P->n), kThreads, 0, s>>>(x, P->n, P->ldx, B, P->xp);
+  }
   P->cnt.kernel_launches += 2;
   int64_t prev_c0 = 0;
   int32_t prevB = 0;
@@ -1111,8 +1136,9 @@ static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, d
     const int32_t kc = (int32_t)std::min<int64_t>(B, ncl - c0l);
     const int64_t c0 = P->col_begin + c0l;
     const int sb = (std::max(kc, prevB) + kThreads - 1) / kThreads;
-    set_components<<<sb, kThreads, 0, s>>>(x, P->eps_cols, c0l, c0, prev_c0, kc, prevB, P->ldx, 1.0, P->xp);
-    TRY(call_f(P, f, ctx, P->Fp, P->xp, kc, s));                         // f(fx1, x1)   jacobians.jl:553 / :594
+    if (COMPLEX) set_components_complex<<<sb, kThreads, 0, s>>>(P->eps_cols, c0l, c0, prev_c0, kc, prevB, sX, P->xp);
+    else set_components<<<sb, kThreads, 0, s>>>(x, P->eps_cols, c0l, c0, prev_c0, kc, prevB, P->ldx, 1.0, P->xp);
+    TRY(call_f(P, f, ctx, P->Fp, P->xp, kc, s));                         // f(fx1, x1)   jacobians.jl:553 / :594 / :629
     if (CENTRAL) {
       set_components<<<sb, kThreads, 0, s>>>(x, P->eps_cols, c0l, c0, 0, kc, 0, P->ldx, -1.0, P->xp);
       TRY(call_f(P, f, ctx, P->Fm, P->xp, kc, s));                       // f(fx, x1)    :596
@@ -1122,8 +1148,8 @@ static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, d
     dim3 grid((unsigned)gx, (unsigned)kc);
     {
       ScatterTimer tm(P, s);
-      diff_columns<CENTRAL><<<grid, kThreads, 0, s>>>(P->Fp, CENTRAL ? P->Fm : vfx, P->eps_cols, c0l, kc, P->m, P->ldF, P->ldJ,
-                                                      J + c0l * P->ldJ);
+      diff_columns<MODE><<<grid, kThreads, 0, s>>>(P->Fp, CENTRAL ? P->Fm : vfx, P->eps_cols, c0l, kc, P->m, sF, P->ldJ,
+                                                   J + c0l * P->ldJ);
     }
     P->cnt.kernel_launches += 2;
     P->cnt.scatter_launches += 1;
@@ -1139,14 +1165,15 @@ extern "C" {
 static fdb_status jacobian_eager(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, double *d_J, double *fx,
                                  const double *d_f_in, double relstep, double absstep, double dir, cudaStream_t s) {
   if (P->sp_kind == SP_NONE) {
-    return P->fdtype == FDB_CENTRAL ? run_dense<true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
-                                    : run_dense<false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    if (P->fdtype == FDB_CENTRAL) return run_dense<kCentral>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    if (P->fdtype == FDB_COMPLEX) return run_dense<kComplex>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    return run_dense<kForward>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
   }
   return dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
     using CT = decltype(tag);
-    return P->fdtype == FDB_CENTRAL
-               ? run_colored<CT, true>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s)
-               : run_colored<CT, false>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    if (P->fdtype == FDB_CENTRAL) return run_colored<CT, kCentral>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    if (P->fdtype == FDB_COMPLEX) return run_colored<CT, kComplex>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
+    return run_colored<CT, kForward>(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
   });
 }
 
@@ -1154,6 +1181,8 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
                         const double *d_f_in, double relstep, double absstep, double dir, void *stream) {
   if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
   if ((P->n > 0 && !d_x) || (P->j_len > 0 && !d_J)) return fail(FDB_ERR_INVALID, "NULL x or J");
+  if (P->fdtype == FDB_COMPLEX && !P->complex_entry)
+    return fail(FDB_ERR_INVALID, "this plan is a complex-step plan: call fdb_jacobian_complex with a complex128 callback");
   DeviceGuard g(P->device);
   if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
   cudaStream_t s = (cudaStream_t)stream;
@@ -1201,6 +1230,16 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
     st = jacobian_eager(P, f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, s);
   }
   if (st == FDB_OK) P->cnt.jacobians += 1;
+  return st;
+}
+
+fdb_status fdb_jacobian_complex(fdb_plan *P, fdb_fn_c f, void *ctx, const double *d_x, double *d_J, void *stream) {
+  if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
+  if (P->fdtype != FDB_COMPLEX) return fail(FDB_ERR_INVALID, "fdb_jacobian_complex needs a plan created with fdtype = FDB_COMPLEX");
+  // same C signature up to the element type of the buffers: the complex128 slabs are handed over as raw pointers
+  P->complex_entry = true;
+  const fdb_status st = fdb_jacobian(P, reinterpret_cast<fdb_fn>(f), ctx, d_x, d_J, nullptr, nullptr, 0.0, 0.0, 1.0, stream);
+  P->complex_entry = false;
   return st;
 }
 

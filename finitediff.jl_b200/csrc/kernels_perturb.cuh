@@ -107,6 +107,51 @@ perturb_colors(const PerturbArgs a) {
   }
 }
 
+// ---- complex step (jacobians.jl:634,644):  x1 = x + im*eps*(color==k)  ...  x1 = x1 - im*eps*(color==k) ----
+// The point is complex128 (re, im interleaved): re = x, im = eps on the colour's columns, 0 elsewhere.  No drift: the
+// imaginary part returns to exactly 0 ((0+eps)-eps) and the real part is never touched.  xp is addressed in DOUBLES:
+// point b starts at xp + b*ldx with ldx = 2 * (complex elements per point).
+template <typename CT, int NP>
+__global__ void __launch_bounds__(kThreads)
+perturb_complex(const PerturbArgs a) {
+  const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < a.n; j += stride) {
+    const double v = ld_stream(a.x + j);
+    const uint32_t c = (uint32_t)jcolor[j];
+    const double e = c < (uint32_t)a.C ? __ldg(a.eps + c) : 0.0;
+#pragma unroll
+    for (int b = 0; b < NP; ++b) {
+      if (NP > 1 && b >= a.kcount) break;
+      st_stream2(a.xp + (int64_t)b * a.ldx + 2 * j, v, c == (uint32_t)a.k[b] ? e : 0.0);
+    }
+  }
+}
+
+// dense complex branch (jacobians.jl:627-631): X[b] = complex(x), then only the imaginary part of one component per copy
+__global__ void __launch_bounds__(kThreads)
+replicate_x_complex(const double *__restrict__ x, int64_t n, int64_t ldx /* doubles */, int32_t B, double *__restrict__ X) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += stride) {
+    const double v = x[j];
+    for (int32_t b = 0; b < B; ++b) st_stream2(X + (int64_t)b * ldx + 2 * j, v, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+set_components_complex(const double *__restrict__ eps_local, int64_t col0_local, int64_t c0, int64_t prev_c0, int32_t B,
+                       int32_t prevB, int64_t ldx /* doubles */, double *__restrict__ X) {
+  const int b = blockIdx.x * kThreads + threadIdx.x;
+  if (b < prevB) X[(int64_t)b * ldx + 2 * (prev_c0 + b) + 1] = 0.0;                      // x1[i] = x1_save   :631
+  if (b < B) X[(int64_t)b * ldx + 2 * (c0 + b) + 1] = eps_local[col0_local + b];          // x1_save + im*eps :628
+}
+
+__global__ void __launch_bounds__(kThreads)
+fill_value(double *__restrict__ p, int64_t n, double v) {
+  const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 // ---- dense-column branch (jacobians.jl:548-557, :590-598) ----
 // The batch buffer X[b] (b < B) holds B copies of x; per batch only the one perturbed component per copy changes.
 

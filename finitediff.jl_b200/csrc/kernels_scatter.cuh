@@ -1,15 +1,15 @@
 // kernels_scatter.cuh — K5: the fused divided-difference + decompression ("diff+scatter") kernels.
 //
-// Reference, per colour k (jacobians.jl:565-572 / :607-614):
-//     @. vfx1 = (vfx1 - vfx) / eps_k            (a full-length pass, in place)
+// Reference, per colour k (jacobians.jl:565-572 / :607-614 / :636-643):
+//     @. vfx1 = (vfx1 - vfx) / eps_k            (a full-length pass, in place; complex step: vfx = imag(vfx)/eps)
 //     _colorediteration!(J, ..., vfx1, colorvec, k, n)   -> for every structural entry (r,c) with colorvec[c]==k:
 //                                                           J[r,c] = vfx1[r]
 // (CSC same-pattern: ext/FiniteDiffSparseArraysExt.jl:38-47; CSC->J[r,c]: :20-28; COO: src/iteration_utils.jl:25-32;
-//  banded whole-band: ext/FiniteDiffBandedMatricesExt.jl:13-27; dense column: jacobians.jl:555,597.)
+//  banded whole-band: ext/FiniteDiffBandedMatricesExt.jl:13-27; dense column: jacobians.jl:555,597,630.)
 //
 // B200 formulation: the f! outputs of the colours of a group stay resident as slabs F[slab][m]; ONE launch walks J's
 // value storage in storage order, and for every structural entry e (row r_e, colour k_e) computes
-//     J[dest(e)] = (F[slab(k_e)][r_e] - fx[r_e]) / eps[k_e]          (central: (Fp - Fm) / (2 eps))
+//     J[dest(e)] = (F[slab(k_e)][r_e] - fx[r_e]) / eps[k_e]          (central: (Fp - Fm) / (2 eps); complex: imag(F)/eps)
 // at gather time — the divided difference is never materialised, index/colour streams are read once, fully
 // coalesced, and J is written once with full sectors (per-colour launches would touch every sector of nzval C times).
 // IEEE subtraction and division are the same operations the reference performs, so values are bit-identical
@@ -19,6 +19,19 @@
 
 namespace fdb {
 
+// finite-difference flavour of a kernel instantiation
+enum : int { kForward = 0, kCentral = 1, kComplex = 2 };
+
+// The quotient the reference stores.  `hi` = the colour's slab (f(x+eps e_k); complex step: complex128 interleaved,
+// so the imaginary part of row r sits at 2r+1 and ldF counts doubles), `lo` = f(x) (forward) / the minus slab (central).
+template <int MODE>
+__device__ __forceinline__ double fd_quotient(const double *__restrict__ hi, const double *__restrict__ lo, int64_t r,
+                                              double e) {
+  if (MODE == kComplex) return __ldg(hi + 2 * r + 1) / e;            // jacobians.jl:636  imag(vfx) / epsilon
+  const double d = __ldg(hi + r) - __ldg(lo + r);
+  return d / (MODE == kCentral ? 2 * e : e);                         // :565 (vfx1-vfx)/epsilon ; :607 .../2epsilon
+}
+
 // r1 tuning on B200 (C2, ncu): 8 resident blocks/SM (32 registers) 133 us, 6 blocks (40 regs) 150 us, 5 blocks 165 us
 constexpr int kScatterMinBlocks = 8;
 constexpr int kSmemTable = 1024;       // colours whose (slab, eps) tables are staged in (dynamic) shared memory
@@ -27,8 +40,8 @@ struct ScatterArgs {
   const int32_t *row;        // [E] 0-based row of entry e
   const void *ecolor;        // [E] 0-based colour of the entry's column (CT)
   const int64_t *dest;       // [E] destination offset, or null => identity (nzval[e])
-  const double *fx;          // forward: vfx = f(x) [m]; central: unused
-  const double *Fp;          // slabs [G][ldF]: f(x + eps_k e_k)
+  const double *fx;          // forward: vfx = f(x) [m]; otherwise unused
+  const double *Fp;          // slabs [G][ldF]: f(x + eps_k e_k)   (complex step: complex128 slabs, ldF in doubles)
   const double *Fm;          // central: slabs f(x - eps_k e_k)
   const double *eps;         // [C]
   const int32_t *local_of;   // [C] colour -> local index on this rank, -1 if not owned
@@ -69,7 +82,7 @@ __device__ __forceinline__ ScatterTables scatter_tables(const ScatterArgs &a, un
 }
 
 // value of one structural entry; returns false when this launch does not own the entry
-template <bool CENTRAL>
+template <int MODE>
 __device__ __forceinline__ bool entry_value(const ScatterArgs &a, const ScatterTables &t, int32_t r, uint32_t k, double &v) {
   v = 0.0;
   if (k >= (uint32_t)a.C) return a.write_invalid_zero != 0;
@@ -83,14 +96,7 @@ __device__ __forceinline__ bool entry_value(const ScatterArgs &a, const ScatterT
     e = __ldg(a.eps + k);
   }
   if (slab < 0) return false;
-  const double hi = __ldg(a.Fp + (int64_t)slab * a.ldF + r);
-  if (CENTRAL) {
-    const double lo = __ldg(a.Fm + (int64_t)slab * a.ldF + r);
-    v = (hi - lo) / (2 * e);                       // jacobians.jl:607  (vfx1 - vfx) / 2epsilon
-  } else {
-    const double lo = __ldg(a.fx + r);
-    v = (hi - lo) / e;                             // jacobians.jl:565  (vfx1 - vfx) / epsilon
-  }
+  v = fd_quotient<MODE>(a.Fp + (int64_t)slab * a.ldF, MODE == kCentral ? a.Fm + (int64_t)slab * a.ldF : a.fx, r, e);
   return true;
 }
 
@@ -98,21 +104,19 @@ __device__ __forceinline__ bool entry_value(const ScatterArgs &a, const ScatterT
 // each lane owns two entry pairs; row ids arrive as one 8-byte load per pair, colours as one narrow load per pair, the
 // four values leave as two 16-byte stores — every warp-level access is a single contiguous run.
 //   FULL = single group on a single rank: every valid colour is resident (slab == colour), no ownership test.
-template <bool CENTRAL, bool FULL>
+template <int MODE, bool FULL>
 __device__ __forceinline__ bool ident_value(const ScatterArgs &a, const ScatterTables &t, int32_t r, uint32_t k, double &v) {
   if (FULL) {
     v = 0.0;
     if (k >= (uint32_t)a.C) return true;            // column without a valid colour: stays 0 (fill_matrix!)
     const double e = t.eps ? t.eps[k] : __ldg(a.eps + k);
-    const double hi = __ldg(a.Fp + (int64_t)k * a.ldF + r);
-    const double lo = CENTRAL ? __ldg(a.Fm + (int64_t)k * a.ldF + r) : __ldg(a.fx + r);
-    v = (hi - lo) / (CENTRAL ? 2 * e : e);           // jacobians.jl:565 / :607
+    v = fd_quotient<MODE>(a.Fp + (int64_t)k * a.ldF, MODE == kCentral ? a.Fm + (int64_t)k * a.ldF : a.fx, r, e);
     return true;
   }
-  return entry_value<CENTRAL>(a, t, r, k, v);
+  return entry_value<MODE>(a, t, r, k, v);
 }
 
-template <typename CT, bool CENTRAL, bool FULL, int MINB>
+template <typename CT, int MODE, bool FULL, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_ident(const ScatterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -132,10 +136,10 @@ diff_scatter_ident(const ScatterArgs a) {
     ld_color_pair<CT>(ct + tid2, ka0, ka1);
     ld_color_pair<CT>(ct + kHalf + tid2, kb0, kb1);
     double va0, va1, vb0, vb1;
-    const bool wa0 = ident_value<CENTRAL, FULL>(a, t, ra.x, ka0, va0);
-    const bool wa1 = ident_value<CENTRAL, FULL>(a, t, ra.y, ka1, va1);
-    const bool wb0 = ident_value<CENTRAL, FULL>(a, t, rb.x, kb0, vb0);
-    const bool wb1 = ident_value<CENTRAL, FULL>(a, t, rb.y, kb1, vb1);
+    const bool wa0 = ident_value<MODE, FULL>(a, t, ra.x, ka0, va0);
+    const bool wa1 = ident_value<MODE, FULL>(a, t, ra.y, ka1, va1);
+    const bool wb0 = ident_value<MODE, FULL>(a, t, rb.x, kb0, vb0);
+    const bool wb1 = ident_value<MODE, FULL>(a, t, rb.y, kb1, vb1);
     if (FULL) {
       if (a.j_aligned) {
         st_stream2(Jt + tid2, va0, va1);
@@ -166,7 +170,7 @@ diff_scatter_ident(const ScatterArgs a) {
   if (rem0 < a.E && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
     for (int64_t e = rem0 + threadIdx.x; e < a.E; e += kThreads) {
       double v;
-      if (ident_value<CENTRAL, FULL>(a, t, a.row[e], (uint32_t)ecolor[e], v)) {
+      if (ident_value<MODE, FULL>(a, t, a.row[e], (uint32_t)ecolor[e], v)) {
         a.J[e] = v;
         for (int p = 0; p < a.n_peers; ++p) a.peers[p][e] = v;
       }
@@ -179,7 +183,7 @@ __device__ __forceinline__ void store_peers(const ScatterArgs &a, int64_t off, d
 }
 
 // Explicit destination per entry (CSC sparsity -> dense / other-pattern CSC J, COO -> dense J or slots).
-template <typename CT, bool CENTRAL>
+template <typename CT, int MODE>
 __global__ void __launch_bounds__(kThreads)
 diff_scatter_dest(const ScatterArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -190,7 +194,7 @@ diff_scatter_dest(const ScatterArgs a) {
     double v;
     // no zero-writes here: J was zero-filled (fill_matrix!) before the first group
     const uint32_t k = (uint32_t)ecolor[e];
-    if (k < (uint32_t)a.C && entry_value<CENTRAL>(a, t, __ldcs(a.row + e), k, v)) {
+    if (k < (uint32_t)a.C && entry_value<MODE>(a, t, __ldcs(a.row + e), k, v)) {
       const int64_t d = __ldcs(a.dest + e);
       a.J[d] = v;
       store_peers(a, d, v);
@@ -201,9 +205,8 @@ diff_scatter_dest(const ScatterArgs a) {
 // ---- per-colour column-list scatter (CSC) ----
 // The literal shape of ext/FiniteDiffSparseArraysExt.jl:38-47 — "for every column of colour k, for every stored entry:
 // nzval[p] = vfx[rowval[p]]" — driven by the per-colour column lists built at plan time, LANES lanes per column.
-// Used when the gather pattern is random (no row locality between consecutive entries): launched right after the
-// colour's f! so its output slab F[k] is still L2-resident and the 8-byte random gathers never reach HBM; also the
-// multi-GPU form (a rank touches only the columns of the colours it owns).
+// Used when a launch would otherwise stream entries it does not own: colours sharded over GPUs (a rank touches only
+// the columns of its colours; the stores to the peers ride in the same kernel) or more colours than resident slabs.
 constexpr int kMaxSegs = 8;
 struct ColScatterArgs {
   const int32_t *cols;       // cols_by_color
@@ -221,7 +224,7 @@ struct ColScatterArgs {
   int32_t seg_slab[kMaxSegs];    // slab index of the colour's f! output
 };
 
-template <bool CENTRAL, int LANES>
+template <int MODE, int LANES>
 __global__ void __launch_bounds__(kThreads)
 diff_scatter_cols(const ColScatterArgs a) {
   constexpr int kColsPerBlock = kThreads / LANES;
@@ -235,15 +238,11 @@ diff_scatter_cols(const ColScatterArgs a) {
     const int32_t k = a.seg_color[s];
     const int32_t p0 = __ldg(a.colptr32 + c), p1 = __ldg(a.colptr32 + c + 1);
     const double e = k >= 0 ? __ldg(a.eps + k) : 1.0;
-    const double denom = CENTRAL ? 2 * e : e;
     const double *hi = a.Fp + (int64_t)a.seg_slab[s] * a.ldF;
-    const double *lo = CENTRAL ? a.Fm + (int64_t)a.seg_slab[s] * a.ldF : a.fx;
+    const double *lo = MODE == kCentral ? a.Fm + (int64_t)a.seg_slab[s] * a.ldF : a.fx;
     for (int32_t p = p0 + sub; p < p1; p += LANES) {
       double v = 0.0;
-      if (k >= 0) {
-        const int32_t r = __ldg(a.row + p);
-        v = (__ldg(hi + r) - __ldg(lo + r)) / denom;      // jacobians.jl:565 / :607 fused with ext/..SparseArraysExt.jl:44
-      }
+      if (k >= 0) v = fd_quotient<MODE>(hi, lo, __ldg(a.row + p), e);   // fused with ext/..SparseArraysExt.jl:44
       const int64_t d = a.dest ? __ldg(a.dest + p) : (int64_t)p;
       a.J[d] = v;
       for (int q = 0; q < a.n_peers; ++q) a.peers[q][d] = v;
@@ -265,15 +264,30 @@ struct BandArgs {
   int32_t to_dense;          // 1: J is dense column-major (ldJ), only in-matrix slots are written
   int64_t ldF, ldJ;
   int64_t m, n, l, u;
-  int64_t cols_per_tile, chunks_per_col;   // tiling of the (l+u+1) x n band
+  int64_t cols_per_tile;     // narrow-band tiling: whole columns per block step
 };
+
+__device__ __forceinline__ void band_color_lookup(const BandArgs &a, uint32_t k, bool tables, const int32_t *s_slab,
+                                                  const double *s_eps, int32_t &slab, double &e) {
+  slab = -1;
+  e = 1.0;
+  if (k < (uint32_t)a.C) {
+    if (tables) { slab = s_slab[k]; e = s_eps[k]; }
+    else {
+      const int32_t lo = __ldg(a.local_of + k);
+      slab = lo < 0 ? -1 : lo - a.l0;
+      if (slab >= a.G) slab = -1;
+      e = __ldg(a.eps + k);
+    }
+  }
+}
 
 // Wide bands (l+u+1 >= 64): ONE WARP PER COLUMN.  A band column is a contiguous run of l+u+1 slots whose sources
 // F[slab][c-u .. c+l] are contiguous too; the warp walks it 32 slots at a time (256-byte coalesced stores, coalesced
-// L2-resident gathers), 4 steps in flight.  The per-column work (colour -> slab, eps) is one uniform lookup from
-// shared-memory tables, amortised over the whole column (r1: the per-1024-slot tile version spent most of its time in
-// that dependent-load prologue: 8.1 ms for C3; see profiles/).
-template <typename CT, bool CENTRAL>
+// L2-resident gathers).  The per-column work (colour -> slab, eps) is one uniform lookup from shared-memory tables,
+// amortised over the whole column (r1: the per-1024-slot tile version spent most of its time in that dependent-load
+// prologue: 8.1 ms for C3 vs 3.4 ms; see profiles/).
+template <typename CT, int MODE>
 __global__ void __launch_bounds__(kThreads, 6)
 diff_scatter_band_wide(const BandArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -296,37 +310,29 @@ diff_scatter_band_wide(const BandArgs a) {
   const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
   for (int64_t c = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); c < a.n; c += nwarps) {
     const uint32_t k = (uint32_t)jcolor[c];
-    int32_t slab = -1;
-    double e = 1.0;
-    if (k < (uint32_t)a.C) {
-      if (tables) { slab = s_slab[k]; e = s_eps[k]; }
-      else {
-        const int32_t lo = __ldg(a.local_of + k);
-        slab = lo < 0 ? -1 : lo - a.l0;
-        if (slab >= a.G) slab = -1;
-        e = __ldg(a.eps + k);
-      }
-    }
+    int32_t slab;
+    double e;
+    band_color_lookup(a, k, tables, s_slab, s_eps, slab, e);
     const bool owned = slab >= 0;
     const bool zero_col = k >= (uint32_t)a.C && a.write_other && !a.to_dense;   // no valid colour: stays 0 (fill_matrix!)
     if (!owned && !zero_col) continue;                                         // another group's / rank's column
-    const double denom = CENTRAL ? 2 * e : e;
-    const double *__restrict__ hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF + (c - a.u);
-    const double *__restrict__ lo = (CENTRAL ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx) + (c - a.u);
-    // in-matrix slots: rows r = c-u+d in [0, m)  <=>  d in [d_lo, d_hi); the corner slots outside the matrix get 0
-    const int64_t d_lo64 = a.u - c > 0 ? a.u - c : 0;
-    const int64_t d_hi64 = a.m - c + a.u < w ? a.m - c + a.u : w;
+    const double *__restrict__ hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF;
+    const double *__restrict__ lo = MODE == kCentral ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx;
+    const int64_t r0 = c - a.u;                        // row of slot 0
+    // in-matrix slots: rows r = r0+d in [0, m)  <=>  d in [d_lo, d_hi); the corner slots outside the matrix get 0
+    const int64_t d_lo64 = -r0 > 0 ? -r0 : 0;
+    const int64_t d_hi64 = a.m - r0 < w ? a.m - r0 : w;
     const int wi = (int)w, d_lo = (int)d_lo64, d_hi = (int)(d_hi64 > d_lo64 ? d_hi64 : d_lo64);
     if (a.to_dense) {
-      double *__restrict__ out = a.J + c * a.ldJ + (c - a.u);
+      double *__restrict__ out = a.J + c * a.ldJ + r0;
       if (owned)
-        for (int d = d_lo + lane; d < d_hi; d += 32) out[d] = (__ldg(hi + d) - __ldg(lo + d)) / denom;
+        for (int d = d_lo + lane; d < d_hi; d += 32) out[d] = fd_quotient<MODE>(hi, lo, r0 + d, e);
     } else {
       double *__restrict__ out = a.J + c * w;
       for (int d = lane; d < d_lo; d += 32) st_stream(out + d, 0.0);
       if (owned) {
 #pragma unroll 2
-        for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, (__ldg(hi + d) - __ldg(lo + d)) / denom);
+        for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, fd_quotient<MODE>(hi, lo, r0 + d, e));
       } else {
         for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, 0.0);
       }
@@ -335,91 +341,46 @@ diff_scatter_band_wide(const BandArgs a) {
   }
 }
 
-template <typename CT, bool CENTRAL>
+// Narrow bands: a tile = cols_per_tile whole columns, flat index inside the tile
+template <typename CT, int MODE>
 __global__ void __launch_bounds__(kThreads)
 diff_scatter_band(const BandArgs a) {
   const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
   const int64_t w = a.l + a.u + 1;
-  if (a.chunks_per_col > 0) {
-    // wide band: one tile = kThreads*4 consecutive slots of one column
-    const int64_t ntiles = a.n * a.chunks_per_col;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t c = tile / a.chunks_per_col;
-      const int64_t d0 = (tile - c * a.chunks_per_col) * (kThreads * 4);
+  const int64_t ntiles = (a.n + a.cols_per_tile - 1) / a.cols_per_tile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t c0 = tile * a.cols_per_tile;
+    int64_t ncol = a.n - c0;
+    if (ncol > a.cols_per_tile) ncol = a.cols_per_tile;
+    const int32_t total = (int32_t)(ncol * w);
+    const int32_t w32 = (int32_t)w;
+    for (int32_t t = threadIdx.x; t < total; t += kThreads) {
+      const int32_t cc = t / w32;
+      const int32_t d = t - cc * w32;
+      const int64_t c = c0 + cc;
+      const int64_t r = c + d - a.u;
+      const bool in = r >= 0 && r < a.m;
       const uint32_t k = (uint32_t)jcolor[c];
-      int32_t slab = -1;
-      double e = 1.0;
-      if (k < (uint32_t)a.C) {
-        const int32_t lo = __ldg(a.local_of + k);
-        slab = lo < 0 ? -1 : lo - a.l0;
-        if (slab >= a.G) slab = -1;
-        e = __ldg(a.eps + k);
-      }
-      const bool owned = slab >= 0;
-      const bool zero_col = k >= (uint32_t)a.C && a.write_other && !a.to_dense;  // no valid colour: stays 0 (fill_matrix!)
-      if (!owned && !zero_col) continue;   // a column of another group / rank: not ours to write
-      const double denom = CENTRAL ? 2 * e : e;
-      const double *hi = a.Fp + (int64_t)(owned ? slab : 0) * a.ldF;
-      const double *lo = CENTRAL ? a.Fm + (int64_t)(owned ? slab : 0) * a.ldF : a.fx;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int64_t d = d0 + t * kThreads + threadIdx.x;
-        if (d >= w) break;
-        const int64_t r = c + d - a.u;
-        const bool in = r >= 0 && r < a.m;
-        double v = 0.0;
-        if (owned && in) v = (__ldg(hi + r) - __ldg(lo + r)) / denom;
-        if (a.to_dense) {
-          if (owned && in) a.J[c * a.ldJ + r] = v;
-        } else {
-          st_stream(a.J + c * w + d, v);   // corner slots outside the matrix get 0
-        }
-      }
-    }
-  } else {
-    // narrow band: a tile = cols_per_tile whole columns, flat index inside the tile
-    const int64_t ntiles = (a.n + a.cols_per_tile - 1) / a.cols_per_tile;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t c0 = tile * a.cols_per_tile;
-      int64_t ncol = a.n - c0;
-      if (ncol > a.cols_per_tile) ncol = a.cols_per_tile;
-      const int32_t total = (int32_t)(ncol * w);
-      const int32_t w32 = (int32_t)w;
-      for (int32_t t = threadIdx.x; t < total; t += kThreads) {
-        const int32_t cc = t / w32;
-        const int32_t d = t - cc * w32;
-        const int64_t c = c0 + cc;
-        const int64_t r = c + d - a.u;
-        const bool in = r >= 0 && r < a.m;
-        const uint32_t k = (uint32_t)jcolor[c];
-        int32_t slab = -1;
-        double e = 1.0;
-        if (k < (uint32_t)a.C) {
-          const int32_t lo = __ldg(a.local_of + k);
-          slab = lo < 0 ? -1 : lo - a.l0;
-          if (slab >= a.G) slab = -1;
-          e = __ldg(a.eps + k);
-        }
-        double v = 0.0;
-        if (in && slab >= 0) {
-          const double hi = __ldg(a.Fp + (int64_t)slab * a.ldF + r);
-          const double lo = CENTRAL ? __ldg(a.Fm + (int64_t)slab * a.ldF + r) : __ldg(a.fx + r);
-          v = (hi - lo) / (CENTRAL ? 2 * e : e);
-        }
-        if (a.to_dense) {
-          if (in && slab >= 0) a.J[c * a.ldJ + r] = v;
-        } else if (slab >= 0) {
-          a.J[c0 * w + t] = v;                       // owned column: whole data column (corner slots get 0)
-        } else if (a.write_other && k >= (uint32_t)a.C) {
-          a.J[c0 * w + t] = 0.0;                     // column without a valid colour: stays zero (fill_matrix!)
-        }
+      int32_t slab;
+      double e;
+      band_color_lookup(a, k, false, nullptr, nullptr, slab, e);
+      double v = 0.0;
+      if (in && slab >= 0)
+        v = fd_quotient<MODE>(a.Fp + (int64_t)slab * a.ldF, MODE == kCentral ? a.Fm + (int64_t)slab * a.ldF : a.fx, r, e);
+      if (a.to_dense) {
+        if (in && slab >= 0) a.J[c * a.ldJ + r] = v;
+      } else if (slab >= 0) {
+        a.J[c0 * w + t] = v;                       // owned column: whole data column (corner slots get 0)
+      } else if (a.write_other && k >= (uint32_t)a.C) {
+        a.J[c0 * w + t] = 0.0;                     // column without a valid colour: stays zero (fill_matrix!)
       }
     }
   }
 }
 
-// ---- dense column branch: J[:, c] = (fx1 - fx)/eps_c  (jacobians.jl:555) or (fx1 - fx_minus)/(2 eps_c) (:597) ----
-template <bool CENTRAL>
+// ---- dense column branch: J[:, c] = (fx1 - fx)/eps_c (jacobians.jl:555), (fx1 - fx_minus)/(2 eps_c) (:597),
+//      imag(fx)/eps (:630) ----
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx, const double *__restrict__ eps_local,
              int64_t col0_local, int32_t B, int64_t m, int64_t ldF, int64_t ldJ, double *__restrict__ Jcols) {
@@ -427,13 +388,12 @@ diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx,
   const int b = blockIdx.y;
   if (b >= B) return;
   const double e = eps_local[col0_local + b];
-  const double denom = CENTRAL ? 2 * e : e;
   const double *hi = Fp + (int64_t)b * ldF;
-  const double *lo = CENTRAL ? Fm_or_fx + (int64_t)b * ldF : Fm_or_fx;
+  const double *lo = MODE == kCentral ? Fm_or_fx + (int64_t)b * ldF : Fm_or_fx;
   double *out = Jcols + (int64_t)b * ldJ;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < m; i += stride)
-    st_stream(out + i, (ld_stream(hi + i) - __ldg(lo + i)) / denom);
+    st_stream(out + i, fd_quotient<MODE>(hi, lo, i, e));
 }
 
 }  // namespace fdb

@@ -109,6 +109,26 @@ __global__ void __launch_bounds__(kT) k_rank1(double *__restrict__ fx, const dou
   }
 }
 
+// complex twin of k_tridiag (complex-step path): complex128 arrays as double2; the stencil on re and im separately
+__global__ void __launch_bounds__(kT) k_tridiag_c(double2 *__restrict__ fx, const double2 *__restrict__ x, int64_t n,
+                                                  int64_t ldfx, int64_t ldx) {
+  const double2 *xb = x + (int64_t)blockIdx.y * ldx;
+  double2 *fb = fx + (int64_t)blockIdx.y * ldfx;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+    const double2 c = xb[i];
+    double2 o;
+    if (n == 1) { o.x = mul(-2.0, c.x); o.y = mul(-2.0, c.y); }
+    else if (i == 0) { const double2 r = xb[1]; o.x = add(mul(-2.0, c.x), r.x); o.y = add(mul(-2.0, c.y), r.y); }
+    else if (i == n - 1) { const double2 l = xb[i - 1]; o.x = sub(l.x, mul(2.0, c.x)); o.y = sub(l.y, mul(2.0, c.y)); }
+    else {
+      const double2 l = xb[i - 1], r = xb[i + 1];
+      o.x = add(sub(l.x, mul(2.0, c.x)), r.x);
+      o.y = add(sub(l.y, mul(2.0, c.y)), r.y);
+    }
+    fb[i] = o;
+  }
+}
+
 __device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
   uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -144,6 +164,16 @@ int fdbs_tridiag(void *vctx, double *d_fx, const double *d_x, int64_t batch, int
   if (((uintptr_t)d_x & 15) || ((uintptr_t)d_fx & 15) || (ldx & 1) || (ldfx & 1)) return 2;
   dim3 grid((unsigned)blocks_for((c->n + 1) / 2), (unsigned)batch);
   k_tridiag<<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, ldfx, ldx);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+int fdbs_tridiag_c(void *vctx, void *d_fx, const void *d_x, int64_t batch, int64_t ldfx, int64_t ldx, void *stream) {
+  fdbs_tridiag_ctx *c = (fdbs_tridiag_ctx *)vctx;
+  if (!c || batch < 1 || batch > 65535) return 1;
+  c->calls += batch;
+  if (c->n <= 0) return 0;
+  dim3 grid((unsigned)blocks_for(c->n), (unsigned)batch);
+  k_tridiag_c<<<grid, kT, 0, (cudaStream_t)stream>>>((double2 *)d_fx, (const double2 *)d_x, c->n, ldfx, ldx);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -41,8 +41,10 @@ typedef enum {
   FDB_ERR_NO_DEVICE = 6    /* no CUDA device: this library has NO CPU fallback */
 } fdb_status;
 
-/* fdtype — the Val(:forward)/Val(:central) type parameter of JacobianCache (jacobians.jl:1-9). */
-enum { FDB_FORWARD = 0, FDB_CENTRAL = 1 };
+/* fdtype — the Val(:forward)/Val(:central)/Val(:complex) type parameter of JacobianCache (jacobians.jl:1-9).
+ * FDB_COMPLEX is the complex-step colour loop (jacobians.jl:623-648): x + im*eps, J = imag(f)/eps, eps = eps(Float64);
+ * plans of that type are driven through fdb_jacobian_complex with a complex128 callback. */
+enum { FDB_FORWARD = 0, FDB_CENTRAL = 1, FDB_COMPLEX = 2 };
 
 /* Where `J[row, col] = v` lands — what the reference decides by dispatch on typeof(J). */
 typedef enum {
@@ -62,6 +64,10 @@ typedef enum {
  */
 typedef int (*fdb_fn)(void *ctx, double *d_fx, const double *d_x, int64_t batch, int64_t ldfx, int64_t ldx,
                       void *stream);
+
+/* Complex-step variant of the callback (fdtype = FDB_COMPLEX): d_fx / d_x are complex128 arrays (re, im interleaved:
+ * cuDoubleComplex / ComplexF64); ldfx / ldx count COMPLEX elements.  Same rules as fdb_fn. */
+typedef int (*fdb_fn_c)(void *ctx, void *d_fx, const void *d_x, int64_t batch, int64_t ldfx, int64_t ldx, void *stream);
 
 /* Plan options (all fields have a usable zero default). */
 typedef struct {
@@ -189,6 +195,11 @@ fdb_status fdb_plan_read_timing(fdb_plan *plan, double *scatter_ms, int64_t *sca
  */
 fdb_status fdb_jacobian(fdb_plan *plan, fdb_fn f, void *ctx, const double *d_x, double *d_J, double *d_fx,
                         const double *d_f_in, double relstep, double absstep, double dir, void *stream);
+
+/* Complex-step Jacobian (jacobians.jl:623-648) for plans created with fdtype = FDB_COMPLEX: per colour ONE evaluation
+ * f(fx, x + im*eps*(color==k)) on complex128 device arrays, J = imag(fx)/eps with eps = eps(Float64); no f(x) baseline,
+ * no cancellation (the reference's tests bound the error by 1e-14, finitedifftests.jl:462).  x and J stay real. */
+fdb_status fdb_jacobian_complex(fdb_plan *plan, fdb_fn_c f, void *ctx, const double *d_x, double *d_J, void *stream);
 
 /* Same call with HOST buffers (the reference-facing form: Array x, host J storage): copies x to the device, runs
  * fdb_jacobian on an internal stream, copies J's value storage (and fx when h_fx != NULL) back, then synchronises.

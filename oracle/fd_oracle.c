@@ -5,6 +5,7 @@
  * follows.  Build: gcc -O2 -fno-fast-math -ffp-contract=off [-fopenmp].
  */
 #include "fd_oracle.h"
+#include <complex.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -291,4 +292,51 @@ int fdo_finite_difference_jacobian_cacheless(const fdo_problem *P, double *J, fd
   o->fcalls = oo.fcalls + pre_calls;
   free(c.x1); free(c.x2); free(c.fx); free(c.fx1);
   return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Complex-step colour loop — src/jacobians.jl:623-648 (fdtype == Val(:complex) && returntype <: Real), with the
+ * cache of the complex constructors (:20-32, :60-76, :105-117: x1 and fx are complex, fx1 === nothing) after
+ * copyto!(x1, x) (:519).  epsilon = eps(eltype(x)) (:624); J[r,c] = imag(f(x + im*eps*e_k))[r] / eps.
+ * --------------------------------------------------------------------------------------------------------------- */
+int fdo_finite_difference_jacobian_complex(const fdo_problem *P, double *J, fdo_fn_c f, void *ctx, const double *x,
+                                           const int64_t *colorvec, int nthreads, int64_t *fcalls) {
+  if (!P || !J || !f || !x) return 1;
+  const int64_t m = P->m, n = P->n;
+  const int nt = nthreads > 1 ? nthreads : 1;
+  double _Complex *x1 = (double _Complex *)malloc(sizeof(double _Complex) * (size_t)(n > 0 ? n : 1));
+  double _Complex *fx = (double _Complex *)calloc((size_t)(m > 0 ? m : 1), sizeof(double _Complex));
+  double *vre = (double *)malloc(sizeof(double) * (size_t)(m > 0 ? m : 1));
+  if (!x1 || !fx || !vre) { free(x1); free(fx); free(vre); return 3; }
+  for (int64_t j = 0; j < n; ++j) x1[j] = x[j];                 /* copyto!(x1, x)  :519 */
+  if (P->sp_kind != FDO_SP_NONE) memset(J, 0, (size_t)P->j_len * sizeof(double)); /* fill_matrix! :530-532 */
+  const double epsilon = DBL_EPSILON;                            /* eps(eltype(x))  :624 */
+  const int64_t maxcolor = fdo_max_color(colorvec, n);
+  int64_t calls = 0;
+  for (int64_t color_i = 1; color_i <= maxcolor; ++color_i) {    /* :625 */
+    if (P->sp_kind == FDO_SP_NONE) {
+      /* :626-631 */
+      double _Complex x1_save = x1[color_i - 1];
+      x1[color_i - 1] = x1_save + epsilon * _Complex_I;
+      f(ctx, fx, x1); calls++;
+      double *Jc = J + (color_i - 1) * P->ldJ;
+      for (int64_t i = 0; i < m; ++i) Jc[i] = cimag(fx[i]) / epsilon;   /* :630 */
+      x1[color_i - 1] = x1_save;
+    } else {
+      /* :632-645 */
+      PAR_FOR
+      for (int64_t j = 0; j < n; ++j)
+        if (color_of(colorvec, j) == color_i) x1[j] = x1[j] + epsilon * _Complex_I;          /* :634 */
+      f(ctx, fx, x1); calls++;                                                               /* :635 */
+      PAR_FOR
+      for (int64_t i = 0; i < m; ++i) { vre[i] = cimag(fx[i]) / epsilon; fx[i] = vre[i]; }     /* :636 vfx = imag(vfx)/eps */
+      colorediteration(P, J, vre, colorvec, color_i, nt);                                    /* :637-643 */
+      PAR_FOR
+      for (int64_t j = 0; j < n; ++j)
+        if (color_of(colorvec, j) == color_i) x1[j] = x1[j] - epsilon * _Complex_I;          /* :644 */
+    }
+  }
+  if (fcalls) *fcalls = calls;
+  free(x1); free(fx); free(vre);
+  return 0;
 }

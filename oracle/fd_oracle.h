@@ -30,6 +30,9 @@
 #ifndef FD_ORACLE_H
 #define FD_ORACLE_H
 #include <stdint.h>
+#ifndef __cplusplus
+#include <complex.h>
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -117,6 +120,14 @@ int fdo_finite_difference_jacobian(const fdo_problem *P, double *J, fdo_fn f, vo
  * allocates its own cache. */
 int fdo_finite_difference_jacobian_cacheless(const fdo_problem *P, double *J, fdo_fn f, void *ctx,
                                              double *x, fdo_opts *opts);
+
+/* complex-step variant: jacobians.jl:623-648.  f!(fx, x) works on complex128 arrays; x and J are real.
+ * (C only: the complex callback type is C99 `double _Complex`.) */
+#ifndef __cplusplus
+typedef void (*fdo_fn_c)(void *ctx, double _Complex *fx, const double _Complex *x);
+int fdo_finite_difference_jacobian_complex(const fdo_problem *P, double *J, fdo_fn_c f, void *ctx, const double *x,
+                                           const int64_t *colorvec, int nthreads, int64_t *fcalls);
+#endif
 
 #ifdef __cplusplus
 }

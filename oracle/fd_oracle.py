@@ -243,6 +243,39 @@ def jacobian(P: Problem, J: np.ndarray, f, x: np.ndarray, *, fdtype=FORWARD, rel
     return {"fcalls": int(opts.fcalls), "eps": eps_out[:maxcolor].copy(), "cache": cache}
 
 
+FDO_FN_C = C.CFUNCTYPE(None, C.c_void_p, _f64p, _f64p)   # complex128 arrays as interleaved doubles
+
+
+def jacobian_complex(P: Problem, J: np.ndarray, f, x: np.ndarray, *, colorvec=None, nthreads=1, ctx=None):
+    """Complex-step Jacobian (jacobians.jl:623-648).  f: Python callable f(fx, x) on complex128 numpy views, or a
+    native fdo_fn_c with `ctx`.  Returns dict(fcalls=...)."""
+    L = lib()
+    if not hasattr(L.fdo_finite_difference_jacobian_complex, "_bound"):
+        L.fdo_finite_difference_jacobian_complex.restype = C.c_int
+        L.fdo_finite_difference_jacobian_complex.argtypes = [C.POINTER(_Problem), _f64p, C.c_void_p, C.c_void_p, _f64p,
+                                                             _i64p, C.c_int, C.POINTER(C.c_int64)]
+        L.fdo_finite_difference_jacobian_complex._bound = True
+    cv = _as_i64(colorvec)
+    if ctx is None:
+        m, n = P.m, P.n
+
+        def tramp(_ctx, pfx, px):
+            fx = np.ctypeslib.as_array(pfx, shape=(2 * m,)).view(np.complex128)
+            xx = np.ctypeslib.as_array(px, shape=(2 * n,)).view(np.complex128)
+            f(fx, xx)
+
+        cf = FDO_FN_C(tramp)
+        fptr, cptr = C.cast(cf, C.c_void_p), None
+    else:
+        fptr, cptr = C.cast(f, C.c_void_p), C.cast(C.pointer(ctx), C.c_void_p)
+    calls = C.c_int64(0)
+    rc = L.fdo_finite_difference_jacobian_complex(C.byref(P._c), J.ctypes.data_as(_f64p), fptr, cptr, _p64(x), _pi64(cv),
+                                                  int(nthreads), C.byref(calls))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return {"fcalls": int(calls.value)}
+
+
 def fill_x(n: int, seed: int, nthreads: int = 1) -> np.ndarray:
     x = np.empty(n, np.float64)
     lib().synth_fill_x(_p64(x), n, seed, nthreads)

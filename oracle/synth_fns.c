@@ -111,3 +111,20 @@ void synth_rank1(void *vctx, double *dx, const double *x) {
   PAR_FOR(c->nthreads)
   for (int64_t i = 0; i < n; ++i) dx[i] = x[i] * x[i] + c->w[i] * S;
 }
+
+/* complex twin of synth_tridiag for the complex-step path: the stencil applied to real and imaginary parts
+ * separately (exactly what complex addition / real scaling do), same evaluation order as the real one */
+#include <complex.h>
+void synth_tridiag_c(void *vctx, double _Complex *dx, const double _Complex *x) {
+  const synth_tridiag_ctx *c = (const synth_tridiag_ctx *)vctx;
+  const int64_t n = c->n;
+  const double *xr = (const double *)x;   /* interleaved (re, im) */
+  double *dr = (double *)dx;
+  for (int part = 0; part < 2; ++part) {
+    if (n == 1) { dr[part] = -2 * xr[part]; continue; }
+    PAR_FOR(c->nthreads)
+    for (int64_t i = 1; i < n - 1; ++i) dr[2 * i + part] = (xr[2 * (i - 1) + part] - 2 * xr[2 * i + part]) + xr[2 * (i + 1) + part];
+    dr[part] = -2 * xr[part] + xr[2 + part];
+    dr[2 * (n - 1) + part] = xr[2 * (n - 2) + part] - 2 * xr[2 * (n - 1) + part];
+  }
+}

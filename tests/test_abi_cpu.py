@@ -72,7 +72,7 @@ def test_step_size_helpers_match_oracle(pkg, oracle):
     assert pkg.default_relstep("forward") == 1.4901161193847656e-08      # sqrt(eps)
     assert pkg.default_relstep("central") == 6.0554544523933395e-06      # cbrt(eps)
     with pytest.raises(ValueError):
-        pkg.default_relstep("complex")
+        pkg.default_relstep("hcentral2")
 
 
 def test_no_cpu_fallback(pkg):

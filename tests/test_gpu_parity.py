@@ -702,7 +702,7 @@ def test_error_paths(pkg, dev):
         pkg.make_plan(J, pkg.SparseMatrixCSC(N, N, t64(colptr), t64(badr), None), None, "forward", N, dev)
     # unknown fdtype (epsilons.jl:159-167)
     with pytest.raises(ValueError, match="Unrecognized fdtype"):
-        pkg.JacobianCache(x, "complex")
+        pkg.JacobianCache(x, "hcentral")
     # row-major dense J is not a Julia Matrix
     with pytest.raises(ValueError, match="column-major"):
         pkg.finite_difference_jacobian_(torch.zeros(N, N, dtype=torch.float64, device=dev), lambda a, b: None, x, "forward")

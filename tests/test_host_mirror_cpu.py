@@ -25,7 +25,7 @@ def test_fdtype_validation(pkg):
     from finitediff_jl_b200 import api
     assert api._fdtype_code("forward") == 0 and api._fdtype_code(":central") == 1
     with pytest.raises(ValueError, match="Unrecognized fdtype"):      # epsilons.jl:159-167
-        api._fdtype_code("complex")
+        api._fdtype_code("backward")
     with pytest.raises(ValueError):
         api._fdtype_code("hcentral")
 
