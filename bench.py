@@ -168,6 +168,12 @@ def cpu_jacobian_runner(workload, fdtype, nthreads, scale=1.0):
         ctx = orc.SynthTridiagCtx(n, nthreads)
         cache = dict(x1=np.zeros(n), x2=np.zeros(n), fx=np.zeros(n), fx1=np.zeros(n))
         fn = orc.native_fn("synth_tridiag")
+        if fdtype == "complex":
+            fnc = orc.native_fn("synth_tridiag_c")
+
+            def run_c():
+                return orc.jacobian_complex(P, nz, fnc, x, colorvec=cv, nthreads=nthreads, ctx=ctx)["fcalls"]
+            return run_c, len(rowval), 3, f"N={n} tridiagonal, 3 colours, complex step"
 
         def run():
             return orc.jacobian(P, nz, fn, x, fdtype=fd, colorvec=cv, nthreads=nthreads, ctx=ctx, cache=cache)["fcalls"]
@@ -269,7 +275,7 @@ def build_gpu_problem(pkg, workload, fdtype, dev, rank, world, max_batch, use_gr
         synth.fdbs_fill_x(x.data_ptr(), n, SEED + 2, None)
         J = pkg.SparseMatrixCSC(n, n, colptr, rowval, torch.full((3 * n - 2,), float("nan"), dtype=torch.float64, device=dev))
         ctx = L.TridiagCtx(n, 0)
-        f = native("fdbs_tridiag", ctx, max_batch)
+        f = native("fdbs_tridiag_c" if fdtype == "complex" else "fdbs_tridiag", ctx, max_batch)
         cache = pkg.JacobianCache(x, fdtype, colorvec=cv, sparsity=J, max_batch=max_batch, rank=rank, world=world,
                                   use_graph=use_graph)
         return dict(J=J, f=f, x=x, cache=cache, nnz=3 * n - 2, n=n, ctx=ctx, keep=(colptr, rowval, cv))
@@ -445,7 +451,7 @@ def gpu_arm(args):
 
     # ---- e2e: host buffers through the C ABI (fdb_jacobian_host), H2D x + D2H J values inside the timed region
     e2e = None
-    if world == 1 and workload in ("c1", "c2", "c4") and not args.no_e2e:
+    if world == 1 and workload in ("c1", "c2", "c4") and not args.no_e2e and fdtype != "complex":
         n = prob["n"]
         hx = pkg.pinned_empty(n)
         hx[:] = x.cpu().numpy()
@@ -505,7 +511,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--fdtype", default="forward", choices=["forward", "central"])
+    ap.add_argument("--fdtype", default="forward", choices=["forward", "central", "complex"])
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch eagerly instead of replaying the captured CUDA graph of the call")
@@ -522,6 +528,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
         args.workload = "c2" if max(args.gpus, world) == 1 else "c4"
+    if args.fdtype == "complex" and args.workload not in ("c1", "c2"):
+        raise SystemExit("--fdtype complex is benchmarked on the tridiagonal workloads (c1, c2)")
     if args.steps is None:
         args.steps = 5 if args.impl == "reference" else {"c1": 500, "c2": 200, "c3": 50, "c4": 30, "c5": 5}[args.workload]
     if args.traffic_bytes is None:

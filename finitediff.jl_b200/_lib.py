@@ -76,6 +76,8 @@ ABI_SYMBOLS = {
     "fdb_jacobian": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_jacobian_complex": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "fdb_jacobian_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64]),
+    "fdb_jvp_plan_create": (_int, [_PP, _i64, _i64, C.POINTER(PlanOpts)]),
+    "fdb_jvp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_host_alloc": (_int, [_PP, C.c_size_t]),
     "fdb_host_free": (_int, [_vp]),
     "fdb_device_alloc": (_int, [_PP, C.c_size_t]),

@@ -662,6 +662,86 @@ def finite_difference_jacobian_(J, f, x, cache=None, f_in=None, returntype=None,
 finite_difference_jacobian_b = finite_difference_jacobian_  # alias ("bang")
 
 
+# ------------------------------------------------------------------------------------------------ JVP (src/jvp.jl)
+class JVPCache:
+    """Mirror of FiniteDiff.JVPCache{X1, FX1, fdtype} (src/jvp.jl:14-17): fields x1, fx1.
+
+        JVPCache(x, fdtype="forward")          allocating: x1 = copy(x), fx1 = copy(x)      (:39-44)
+        JVPCache(x, fx1, fdtype="forward")     non-allocating: aliases the arrays passed in (:73-80)
+    """
+
+    def __init__(self, x, fx1=None, fdtype="forward"):
+        if isinstance(fx1, str):
+            fdtype, fx1 = fx1, None
+        self.fdtype = fdtype.lstrip(":") if isinstance(fdtype, str) else fdtype
+        code = _fdtype_code(self.fdtype)
+        if not _is_cuda(x):
+            raise TypeError("JVPCache needs CUDA float64 tensors (this path has no CPU implementation)")
+        if fx1 is None:
+            self.x1, self.fx1 = x.clone(), x.clone()
+        else:
+            self.x1, self.fx1 = x, fx1
+        self._code = code
+        self._plan = None
+
+    def plan(self, m: int, n: int) -> "Plan":
+        if self._plan is None or self._plan_key != (m, n):
+            if self._code == L.FDB_COMPLEX:
+                # jvp.jl:248-250
+                raise ValueError("finite_difference_jvp doesn't support :complex-mode finite diff")
+            h = C.c_void_p()
+            o = _opts(self._code, _device_index(self.x1.device))
+            L.check(L.lib().fdb_jvp_plan_create(C.byref(h), m, n, C.byref(o)))
+            self._plan, self._plan_key = Plan(h.value), (m, n)
+        return self._plan
+
+
+def finite_difference_jvp_(jvp, f, x, v, cache=None, f_in=None, *, relstep=None, absstep=None, dir=True, stream=None):
+    """finite_difference_jvp!(jvp, f, x, v, cache::JVPCache, f_in=nothing; relstep, absstep, dir) (src/jvp.jl:238-274), or
+    — when `cache` is None or an fdtype string — the cache-less form (:198-216).
+    jvp[m], x[n], v[n]: float64 CUDA tensors; f(fx, x) as for the Jacobian.  Returns None."""
+    if isinstance(cache, str) or cache is None:
+        fd = cache if isinstance(cache, str) else "forward"
+        xv = x.reshape(-1)
+        if f_in is not None:
+            c = JVPCache(xv.clone(), f_in.reshape(-1).clone(), fd)                      # JVPCache(x, f_in, fdtype)  :209
+            return finite_difference_jvp_(jvp, f, x, v, c, c.fx1, relstep=relstep, absstep=absstep, stream=stream)
+        c = JVPCache(xv, fd)                                                            # :210-215 (f(fx,x) runs inside)
+        if jvp.numel() != xv.numel():
+            c.fx1 = torch.zeros(jvp.numel(), dtype=torch.float64, device=x.device)
+        return finite_difference_jvp_(jvp, f, x, v, c, None, relstep=relstep, absstep=absstep, stream=stream)
+    if not isinstance(cache, JVPCache):
+        raise TypeError("cache must be a JVPCache, an fdtype string, or None")
+    for t in (jvp, x, v):
+        if not _is_cuda(t) or t.dtype != torch.float64:
+            raise TypeError("jvp, x, v must be float64 CUDA tensors: the B200 path has no CPU implementation")
+    xv, vv, jv = x.reshape(-1), v.reshape(-1), jvp.reshape(-1)
+    if not (xv.is_contiguous() and vv.is_contiguous() and jv.is_contiguous()):
+        raise ValueError("jvp, x, v must be contiguous")
+    n, m = xv.numel(), jv.numel()
+    if vv.numel() != n:
+        raise ValueError("length(v) != length(x)")
+    plan = cache.plan(m, n)
+    if cache.x1.numel() != n or cache.fx1.numel() != m:
+        raise ValueError("JVPCache arrays do not match length(x) / length(jvp)")
+    addr, ctx, pyfn = _as_fn(f, m, n, x.device, 1)
+    if stream is None:
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+    fin_ptr = None
+    if f_in is not None and cache._code == L.FDB_FORWARD:
+        fin_ptr = f_in.reshape(-1).data_ptr()
+    with torch.cuda.device(x.device):
+        st = L.lib().fdb_jvp(plan.handle, addr, ctx, jv.data_ptr(), xv.data_ptr(), vv.data_ptr(), cache.x1.data_ptr(),
+                             cache.fx1.data_ptr(), fin_ptr, 0.0 if relstep is None else float(relstep),
+                             0.0 if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
+    if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
+        exc, pyfn.exc = pyfn.exc, None
+        raise exc
+    L.check(st)
+    cache._last_plan = plan
+    return None
+
+
 def _shape_of(J):
     if isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal)):
         return J.shape

@@ -22,6 +22,7 @@
 #include "kernels_perturb.cuh"
 #include "kernels_plan.cuh"
 #include "kernels_scatter.cuh"
+#include "kernels_jvp.cuh"
 
 using namespace fdb;
 
@@ -51,7 +52,7 @@ static fdb_status fail(fdb_status st, const char *fmt, ...) {
     if (s__ != FDB_OK) return s__;   \
   } while (0)
 
-enum { SP_NONE = 0, SP_CSC = 1, SP_COO = 3, SP_BANDED = 4 };
+enum { SP_NONE = 0, SP_CSC = 1, SP_COO = 3, SP_BANDED = 4, SP_JVP = 5 };
 
 struct DeviceGuard {
   int prev = -1;
@@ -771,7 +772,7 @@ fdb_status fdb_plan_color_owner(const fdb_plan *P, int32_t *owner_out, int64_t c
 fdb_status fdb_plan_get_eps(fdb_plan *P, double *h_eps, int64_t cap, void *stream) {
   if (!P || !h_eps) return fail(FDB_ERR_INVALID, "NULL argument");
   DeviceGuard g(P->device);
-  const int64_t count = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : P->C;
+  const int64_t count = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : P->C;   // JVP plans: C == 1
   if (cap < count) return fail(FDB_ERR_INVALID, "h_eps too small (%lld < %lld)", (long long)cap, (long long)count);
   const double *src = P->sp_kind == SP_NONE ? P->eps_cols : P->eps;
   if (count > 0) {
@@ -1181,6 +1182,7 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
                         const double *d_f_in, double relstep, double absstep, double dir, void *stream) {
   if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
   if ((P->n > 0 && !d_x) || (P->j_len > 0 && !d_J)) return fail(FDB_ERR_INVALID, "NULL x or J");
+  if (P->sp_kind == SP_JVP) return fail(FDB_ERR_INVALID, "this is a JVP plan: call fdb_jvp");
   if (P->fdtype == FDB_COMPLEX && !P->complex_entry)
     return fail(FDB_ERR_INVALID, "this plan is a complex-step plan: call fdb_jacobian_complex with a complex128 callback");
   DeviceGuard g(P->device);
@@ -1241,6 +1243,72 @@ fdb_status fdb_jacobian_complex(fdb_plan *P, fdb_fn_c f, void *ctx, const double
   const fdb_status st = fdb_jacobian(P, reinterpret_cast<fdb_fn>(f), ctx, d_x, d_J, nullptr, nullptr, 0.0, 0.0, 1.0, stream);
   P->complex_entry = false;
   return st;
+}
+
+// ------------------------------------------------------------------------------------------------ JVP (src/jvp.jl:238-274)
+fdb_status fdb_jvp_plan_create(fdb_plan **plan, int64_t m, int64_t n, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, m, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  if (P->fdtype == FDB_COMPLEX) {
+    free_plan(P); *plan = nullptr;
+    return fail(FDB_ERR_UNSUPPORTED, "finite_difference_jvp doesn't support :complex-mode finite diff");   // jvp.jl:248-250
+  }
+  P->sp_kind = SP_JVP;
+  P->C = 1;
+  P->ldF = std::max<int64_t>(2, (m + 1) & ~(int64_t)1);
+  P->ldx = std::max<int64_t>(2, (n + 1) & ~(int64_t)1);
+  int64_t nb = std::max<int64_t>(1, std::min<int64_t>((n + kTile - 1) / kTile, (int64_t)P->sm_count * 8));
+  P->eps_blocks = (int)nb;
+  PLAN_TRY(P->alloc_t(&P->partial, (size_t)nb));
+  PLAN_TRY(P->alloc_t(&P->ticket, 4));
+  cudaMemset(P->ticket, 0, 16);
+  PLAN_TRY(P->alloc_t(&P->eps, 2));
+  PLAN_TRY(P->alloc_t(&P->sumsq, 2));
+  PLAN_TRY(P->alloc_t(&P->fx_own, (size_t)P->ldF));
+  PLAN_TRY(P->alloc_t(&P->xp, (size_t)P->ldx));
+  P->alg_bytes = 24 * n + 24 * m;   // dot: 16n; point: 16n read + 8n write; quotient: 16m read + 8m write
+  return FDB_OK;
+}
+
+fdb_status fdb_jvp(fdb_plan *P, fdb_fn f, void *ctx, double *d_jvp, const double *d_x, const double *d_v, double *d_x1,
+                   double *d_fx1, const double *d_f_in, double relstep, double absstep, double dir, void *stream) {
+  if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
+  if (P->sp_kind != SP_JVP) return fail(FDB_ERR_INVALID, "not a JVP plan (fdb_jvp_plan_create)");
+  if ((P->n > 0 && (!d_x || !d_v)) || (P->m > 0 && !d_jvp)) return fail(FDB_ERR_INVALID, "NULL jvp, x or v");
+  DeviceGuard g(P->device);
+  if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);     // jvp.jl:245-246
+  if (!(absstep > 0)) absstep = relstep;
+  double *x1 = d_x1 ? d_x1 : P->xp;
+  double *fx1 = d_fx1 ? d_fx1 : P->fx_own;
+  const bool central = P->fdtype == FDB_CENTRAL;
+  const int64_t n = P->n, m = P->m;
+  const int al_xv = ((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_v)) & 15) == 0;
+  const int al_x1 = al_xv && (reinterpret_cast<uintptr_t>(x1) & 15) == 0;
+  EpsParams prm{central ? 1 : 0, relstep, absstep, dir};
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  const int grid_n = std::min(resident_grid(P, jvp_dot_eps, 0, tiles), P->eps_blocks);
+  jvp_dot_eps<<<grid_n, kThreads, 0, s>>>(d_x, d_v, n, al_xv, prm, P->partial, P->ticket, P->eps, P->sumsq);   // :252-253
+  P->cnt.kernel_launches += 1;
+  const double *base = fx1;
+  if (!central) {
+    if (d_f_in) base = d_f_in;                                      // fx1 = f_in        :257-258
+    else TRY(call_f(P, f, ctx, fx1, d_x, 1, s));                    // f(fx1, x)         :255
+  } else {
+    jvp_point<<<resident_grid(P, jvp_point, 0, tiles), kThreads, 0, s>>>(d_x, d_v, P->eps, 1, x1, n, al_x1);   // x1 = x - eps v :264
+    P->cnt.kernel_launches += 1;
+    TRY(call_f(P, f, ctx, fx1, x1, 1, s));                          // f(fx1, x1)        :265
+  }
+  jvp_point<<<resident_grid(P, jvp_point, 0, tiles), kThreads, 0, s>>>(d_x, d_v, P->eps, 0, x1, n, al_x1);     // x1 = x + eps v :260/:266
+  TRY(call_f(P, f, ctx, d_jvp, x1, 1, s));                          // f(jvp, x1)        :261/:267
+  jvp_quotient<<<P->grid(m), kThreads, 0, s>>>(d_jvp, base, P->eps, central ? 1 : 0, m);                        // :262/:268
+  P->cnt.kernel_launches += 2;
+  CU(cudaGetLastError());
+  P->cnt.jacobians += 1;
+  return FDB_OK;
 }
 
 fdb_status fdb_jacobian_host(fdb_plan *P, fdb_fn f, void *ctx, const double *h_x, double *h_J, double *h_fx,

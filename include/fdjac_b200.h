@@ -207,6 +207,15 @@ fdb_status fdb_jacobian_complex(fdb_plan *plan, fdb_fn_c f, void *ctx, const dou
 fdb_status fdb_jacobian_host(fdb_plan *plan, fdb_fn f, void *ctx, const double *h_x, double *h_J, double *h_fx,
                              const double *h_f_in, double relstep, double absstep, double dir);
 
+/* ---- Jacobian-vector product: finite_difference_jvp!(jvp, f, x, v, cache::JVPCache, f_in; relstep, absstep, dir)
+ *      src/jvp.jl:238-274 — eps from sqrt(abs(dot(x, v))) (computed on the device), forward: f(fx1,x), f(jvp,x+eps v);
+ *      central: f(fx1, x-eps v) then f(jvp, x+eps v).  opts->fdtype selects forward/central (complex is rejected like
+ *      in the reference).  d_x1 / d_fx1 are the JVPCache arrays (n / m doubles; NULL => plan-owned scratch);
+ *      d_f_in: forward only, precomputed f(x). ---- */
+fdb_status fdb_jvp_plan_create(fdb_plan **plan, int64_t m, int64_t n, const fdb_plan_opts *opts);
+fdb_status fdb_jvp(fdb_plan *plan, fdb_fn f, void *ctx, double *d_jvp, const double *d_x, const double *d_v, double *d_x1,
+                   double *d_fx1, const double *d_f_in, double relstep, double absstep, double dir, void *stream);
+
 /* ---- helpers for hosts without their own CUDA bindings ---- */
 fdb_status fdb_host_alloc(void **p, size_t bytes);  /* pinned host memory */
 fdb_status fdb_host_free(void *p);

@@ -340,3 +340,40 @@ int fdo_finite_difference_jacobian_complex(const fdo_problem *P, double *J, fdo_
   free(x1); free(fx); free(vre);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Jacobian-vector product — src/jvp.jl:238-274, cached in-place form finite_difference_jvp!(jvp, f, x, v, cache, f_in).
+ * cache = (x1[n], fx1[m]).  dot(x, v) is BLAS ddot in Julia: restated as a sequential sum (bit-level eps unpinned,
+ * like norm in the Jacobian driver; `eps_override` lets a test pin it).
+ * --------------------------------------------------------------------------------------------------------------- */
+int fdo_finite_difference_jvp(double *jvp, fdo_fn f, void *ctx, const double *x, const double *v, int64_t m, int64_t n,
+                              double *x1, double *fx1, const double *f_in, int fdtype, double relstep, double absstep,
+                              double dir, const double *eps_override, double *eps_out, int64_t *fcalls) {
+  if (!jvp || !f || !x || !v || !x1 || !fx1) return 1;
+  if (fdtype != FDO_FORWARD && fdtype != FDO_CENTRAL) return 2;   /* :248-250 complex rejected; fdtype_error :270 */
+  if (!(relstep > 0)) relstep = fdo_default_relstep(fdtype);      /* :245 */
+  if (!(absstep > 0)) absstep = relstep;                          /* :246 */
+  double d = 0.0;
+  for (int64_t j = 0; j < n; ++j) d += x[j] * v[j];
+  const double tmp = sqrt(fabs(d));                               /* :252 */
+  double epsilon = eps_override ? *eps_override : fdo_compute_epsilon(fdtype, tmp, relstep, absstep, dir); /* :253 */
+  if (eps_out) *eps_out = epsilon;
+  int64_t calls = 0;
+  if (fdtype == FDO_FORWARD) {
+    const double *base = fx1;
+    if (!f_in) { f(ctx, fx1, x); calls++; }                       /* :255 */
+    else base = f_in;                                             /* :257-258 */
+    for (int64_t j = 0; j < n; ++j) x1[j] = x[j] + epsilon * v[j]; /* :260 */
+    f(ctx, jvp, x1); calls++;                                      /* :261 */
+    for (int64_t i = 0; i < m; ++i) jvp[i] = (jvp[i] - base[i]) / epsilon; /* :262 */
+  } else {
+    for (int64_t j = 0; j < n; ++j) x1[j] = x[j] - epsilon * v[j]; /* :264 */
+    f(ctx, fx1, x1); calls++;                                      /* :265 */
+    for (int64_t j = 0; j < n; ++j) x1[j] = x[j] + epsilon * v[j]; /* :266 */
+    f(ctx, jvp, x1); calls++;                                      /* :267 */
+    const double two_eps = 2 * epsilon;
+    for (int64_t i = 0; i < m; ++i) jvp[i] = (jvp[i] - fx1[i]) / two_eps; /* :268 */
+  }
+  if (fcalls) *fcalls = calls;
+  return 0;
+}

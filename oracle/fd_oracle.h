@@ -121,6 +121,11 @@ int fdo_finite_difference_jacobian(const fdo_problem *P, double *J, fdo_fn f, vo
 int fdo_finite_difference_jacobian_cacheless(const fdo_problem *P, double *J, fdo_fn f, void *ctx,
                                              double *x, fdo_opts *opts);
 
+/* Jacobian-vector product, cached in-place form: src/jvp.jl:238-274.  x1[n], fx1[m] are the JVPCache arrays. */
+int fdo_finite_difference_jvp(double *jvp, fdo_fn f, void *ctx, const double *x, const double *v, int64_t m, int64_t n,
+                              double *x1, double *fx1, const double *f_in, int fdtype, double relstep, double absstep,
+                              double dir, const double *eps_override, double *eps_out, int64_t *fcalls);
+
 /* complex-step variant: jacobians.jl:623-648.  f!(fx, x) works on complex128 arrays; x and J are real.
  * (C only: the complex callback type is C99 `double _Complex`.) */
 #ifndef __cplusplus

@@ -276,6 +276,36 @@ def jacobian_complex(P: Problem, J: np.ndarray, f, x: np.ndarray, *, colorvec=No
     return {"fcalls": int(calls.value)}
 
 
+def jvp(f, x: np.ndarray, v: np.ndarray, m: int, *, fdtype=FORWARD, relstep=0.0, absstep=0.0, dir=1.0, f_in=None,
+        eps_override=None, ctx=None):
+    """finite_difference_jvp!(jvp, f, x, v, cache, f_in) (src/jvp.jl:238-274).  Returns dict(jvp, eps, fcalls, x1, fx1)."""
+    L = lib()
+    fn = L.fdo_finite_difference_jvp
+    if not hasattr(fn, "_bound"):
+        fn.restype = C.c_int
+        fn.argtypes = [_f64p, C.c_void_p, C.c_void_p, _f64p, _f64p, C.c_int64, C.c_int64, _f64p, _f64p, _f64p, C.c_int,
+                       C.c_double, C.c_double, C.c_double, _f64p, _f64p, C.POINTER(C.c_int64)]
+        fn._bound = True
+    n = len(x)
+    out = np.zeros(max(m, 1))
+    x1, fx1 = np.zeros(max(n, 1)), np.zeros(max(m, 1))
+    if ctx is None:
+        cf, st = as_fn(f)
+        st["m"], st["n"] = m, n
+        fptr, cptr = C.cast(cf, C.c_void_p), None
+    else:
+        fptr, cptr = C.cast(f, C.c_void_p), C.cast(C.pointer(ctx), C.c_void_p)
+    fin = None if f_in is None else np.ascontiguousarray(f_in, dtype=np.float64)
+    eo = None if eps_override is None else np.array([eps_override], dtype=np.float64)
+    eps_out = np.zeros(1)
+    calls = C.c_int64(0)
+    rc = fn(_p64(out), fptr, cptr, _p64(np.ascontiguousarray(x)), _p64(np.ascontiguousarray(v)), m, n, _p64(x1), _p64(fx1),
+            _p64(fin), fdtype, relstep, absstep, float(dir), _p64(eo), _p64(eps_out), C.byref(calls))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return {"jvp": out[:m], "eps": float(eps_out[0]), "fcalls": int(calls.value), "x1": x1, "fx1": fx1}
+
+
 def fill_x(n: int, seed: int, nthreads: int = 1) -> np.ndarray:
     x = np.empty(n, np.float64)
     lib().synth_fill_x(_p64(x), n, seed, nthreads)
