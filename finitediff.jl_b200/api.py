@@ -28,7 +28,7 @@ import torch
 from . import _lib as L
 
 __all__ = [
-    "SparseMatrixCSC", "BandedMatrix", "Tridiagonal", "NativeFn", "JacobianCache", "Plan",
+    "SparseMatrixCSC", "BandedMatrix", "Tridiagonal", "BandedBlockBandedMatrix", "NativeFn", "JacobianCache", "Plan",
     "finite_difference_jacobian_", "finite_difference_jacobian_b", "resize_", "default_relstep", "compute_epsilon",
     "zeros_colmajor", "pinned_empty",
 ]
@@ -216,6 +216,70 @@ class Tridiagonal:
         b = self.buf.cpu().numpy()
         n = self.n
         return np.diag(b[n - 1: 2 * n - 1]) + np.diag(b[: n - 1], -1) + np.diag(b[2 * n - 1:], 1)
+
+
+class BandedBlockBandedMatrix:
+    """Mirror of BlockBandedMatrices.BandedBlockBandedMatrix: square blocks structure given by `rowblocks` / `colblocks`
+    (block lengths), block bandwidths (l, u) and sub-block bandwidths (lam, mu).  The decompression hook
+    ext/FiniteDiffBlockBandedMatricesExt.jl:16-42 writes, for every column j of block-column J and every block-row
+    K in blockcolrange(J) = max(1,J-u):min(N,J+l), the in-sub-band rows k in max(1,j-mu):min(m_K, j+lam).
+    Storage here: one band-data column of (l+u+1)*(lam+mu+1) slots per matrix column — slot
+    (K-J+u)*(lam+mu+1) + (mu+k-j) for entry (k, j) of block (K, J) (the BlockBandedMatrices layout as documented; the
+    package source is not vendored in the reference tree, so the LAYOUT is this mirror's own — the ENTRY SET and the
+    values are what parity is about, coloring_tests.jl:99-119)."""
+
+    def __init__(self, rowblocks, colblocks, blockbandwidths, subblockbandwidths, data=None, device="cuda"):
+        self.rb, self.cb = [int(b) for b in rowblocks], [int(b) for b in colblocks]
+        (self.l, self.u), (self.lam, self.mu) = blockbandwidths, subblockbandwidths
+        self.m, self.n = sum(self.rb), sum(self.cb)
+        self.w = (self.l + self.u + 1) * (self.lam + self.mu + 1)
+        if data is None:
+            data = torch.zeros(self.w * self.n, dtype=torch.float64, device=device)
+        self.data = data
+        self._nz = None
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def findstructralnz(self):
+        """(rows, cols, slots), 1-based, in the order the reference's hook visits them."""
+        if self._nz is None:
+            ro = np.concatenate([[0], np.cumsum(self.rb)])
+            co = np.concatenate([[0], np.cumsum(self.cb)])
+            sw = self.lam + self.mu + 1
+            rows, cols, slots = [], [], []
+            N_r, N_c = len(self.rb), len(self.cb)
+            for J in range(1, N_c + 1):
+                for K in range(max(1, J - self.u), min(N_r, J + self.l) + 1):
+                    mK = self.rb[K - 1]
+                    for j in range(1, self.cb[J - 1] + 1):
+                        k = np.arange(max(1, j - self.mu), min(mK, j + self.lam) + 1)
+                        if len(k) == 0:
+                            continue
+                        gc = co[J - 1] + j
+                        rows.append(ro[K - 1] + k)
+                        cols.append(np.full(len(k), gc))
+                        slots.append((gc - 1) * self.w + (K - J + self.u) * sw + (self.mu + k - j) + 1)
+            cat = lambda a: np.concatenate(a).astype(np.int64) if a else np.zeros(0, np.int64)
+            self._nz = (cat(rows), cat(cols), cat(slots))
+        return self._nz
+
+    def to_dense(self) -> np.ndarray:
+        rows, cols, slots = self.findstructralnz()
+        d = self.data.cpu().numpy() if isinstance(self.data, torch.Tensor) else np.asarray(self.data)
+        J = np.zeros((self.m, self.n))
+        J[rows - 1, cols - 1] = d[slots - 1]
+        return J
+
+    def matrix_colors(self) -> np.ndarray:
+        """A valid colouring for the full structure: block colour (cycle l+u+1) x sub-band colour (cycle lam+mu+1)
+        — the scheme of ArrayInterface.matrix_colors(::BandedBlockBandedMatrix) for uniform blocks."""
+        sw, bw = self.lam + self.mu + 1, self.l + self.u + 1
+        out = []
+        for J, nb in enumerate(self.cb):
+            out.append((J % bw) * sw + (np.arange(nb) % sw) + 1)
+        return np.concatenate(out).astype(np.int64)
 
 
 def _findstructralnz_dense(A):
@@ -425,6 +489,21 @@ def make_plan(J, sparsity, colorvec, fdtype, x_len: int, device, **plan_kw) -> P
         else:
             raise TypeError(f"unsupported J type {type(J)} for a Tridiagonal sparsity")
         keep += [rows, cols, slots]
+    elif isinstance(sparsity, BandedBlockBandedMatrix):
+        # ext/FiniteDiffBlockBandedMatricesExt.jl:16-42: the hook's (block-row, sub-band) entry set, written by slot
+        rows, cols, slots = sparsity.findstructralnz()
+        if isinstance(J, BandedBlockBandedMatrix):
+            if (J.rb, J.cb, J.l, J.u, J.lam, J.mu) != (sparsity.rb, sparsity.cb, sparsity.l, sparsity.u, sparsity.lam, sparsity.mu):
+                raise ValueError("J and sparsity must have the same block structure")
+            L.check(lib.fdb_plan_create_coo(C.byref(h), sparsity.m, sparsity.n, len(rows), rows.ctypes.data, cols.ctypes.data,
+                                            L.FDB_J_SLOTS, slots.ctypes.data, sparsity.w * sparsity.n, cv_ptr, C.byref(o)))
+        elif isinstance(J, torch.Tensor):
+            m, nn, ld = _dense_ld(J)
+            L.check(lib.fdb_plan_create_coo(C.byref(h), m, nn, len(rows), rows.ctypes.data, cols.ctypes.data,
+                                            L.FDB_J_DENSE, None, ld, cv_ptr, C.byref(o)))
+        else:
+            raise TypeError(f"unsupported J type {type(J)} for a BandedBlockBandedMatrix sparsity")
+        keep += [rows, cols, slots]
     elif isinstance(sparsity, (torch.Tensor, np.ndarray, list)):
         # dense 0/1 prototype: rows/cols from _findstructralnz (jacobians.jl:526-527), J must be dense
         rows, cols = _findstructralnz_dense(sparsity)
@@ -441,7 +520,7 @@ def make_plan(J, sparsity, colorvec, fdtype, x_len: int, device, **plan_kw) -> P
 
 def _has_sparsestruct(J) -> bool:
     """ArrayInterface.has_sparsestruct(J) as used at jacobians.jl:455."""
-    return isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal))
+    return isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal, BandedBlockBandedMatrix))
 
 
 def _j_values(J):
@@ -451,6 +530,8 @@ def _j_values(J):
         return J.data
     if isinstance(J, Tridiagonal):
         return J.buf
+    if isinstance(J, BandedBlockBandedMatrix):
+        return J.data
     return J
 
 
@@ -461,6 +542,8 @@ def _j_key(J):
         return ("band", J.m, J.n, J.l, J.u)
     if isinstance(J, Tridiagonal):
         return ("tri", J.n)
+    if isinstance(J, BandedBlockBandedMatrix):
+        return ("bbb", tuple(J.rb), tuple(J.cb), J.l, J.u, J.lam, J.mu)
     if isinstance(J, torch.Tensor):
         return ("dense", tuple(J.shape), tuple(J.stride()))
     if isinstance(J, np.ndarray):
@@ -471,7 +554,7 @@ def _j_key(J):
 def _sp_key(sp):
     if sp is None:
         return None
-    if isinstance(sp, (SparseMatrixCSC, BandedMatrix, Tridiagonal)):
+    if isinstance(sp, (SparseMatrixCSC, BandedMatrix, Tridiagonal, BandedBlockBandedMatrix)):
         return _j_key(sp)
     if isinstance(sp, torch.Tensor):
         return ("proto", sp.data_ptr(), tuple(sp.shape), sp._version)
@@ -743,7 +826,7 @@ def finite_difference_jvp_(jvp, f, x, v, cache=None, f_in=None, *, relstep=None,
 
 
 def _shape_of(J):
-    if isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal)):
+    if isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal, BandedBlockBandedMatrix)):
         return J.shape
     if isinstance(J, torch.Tensor):
         if J.dim() == 1:

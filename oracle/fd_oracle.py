@@ -106,6 +106,8 @@ def lib():
                                                                _f64p, C.POINTER(_Opts)]
         L.synth_fill_x.restype = None
         L.synth_fill_x.argtypes = [_f64p, C.c_int64, C.c_uint64, C.c_int]
+        L.synth_ellrows.restype = None
+        L.synth_ellrows.argtypes = [C.c_void_p, _f64p, _f64p]
         L.synth_blocked_sum.restype = C.c_double
         L.synth_blocked_sum.argtypes = [_f64p, C.c_int64]
         _lib = L
