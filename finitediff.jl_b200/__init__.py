@@ -12,10 +12,10 @@ The directory name contains a dot, so it is imported through /root/repo/_bootstr
 `finitediff_jl_b200`.
 """
 from . import _lib  # noqa: F401
-from .api import (BandedBlockBandedMatrix, BandedMatrix, JacobianCache, JVPCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
+from .api import (BandedBlockBandedMatrix, BandedMatrix, BlockBandedMatrix, JacobianCache, JVPCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
                   default_relstep, finite_difference_jacobian_, finite_difference_jacobian_b, finite_difference_jvp_,
                   make_plan, pinned_empty, resize_, zeros_colmajor)
 
-__all__ = ["BandedBlockBandedMatrix", "BandedMatrix", "JacobianCache", "JVPCache", "finite_difference_jvp_", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
+__all__ = ["BandedBlockBandedMatrix", "BandedMatrix", "BlockBandedMatrix", "JacobianCache", "JVPCache", "finite_difference_jvp_", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
            "default_relstep", "finite_difference_jacobian_", "finite_difference_jacobian_b", "make_plan",
            "pinned_empty", "resize_", "zeros_colmajor"]

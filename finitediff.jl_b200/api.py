@@ -282,6 +282,16 @@ class BandedBlockBandedMatrix:
         return np.concatenate(out).astype(np.int64)
 
 
+class BlockBandedMatrix(BandedBlockBandedMatrix):
+    """Mirror of BlockBandedMatrices.BlockBandedMatrix: dense blocks inside the block band.  Hook
+    ext/FiniteDiffBlockBandedMatricesExt.jl:44-68: for every column j of block-column J, ALL rows of every block-row K
+    in blockcolrange(J).  Expressed as a BandedBlockBandedMatrix whose sub-block bandwidths cover the whole block."""
+
+    def __init__(self, rowblocks, colblocks, blockbandwidths, data=None, device="cuda"):
+        full = max(max(rowblocks), max(colblocks)) - 1 if len(rowblocks) and len(colblocks) else 0
+        super().__init__(rowblocks, colblocks, blockbandwidths, (full, full), data=data, device=device)
+
+
 def _findstructralnz_dense(A):
     """src/jacobians.jl:473-488: column-major scan of a dense 0/1 prototype."""
     A = np.asarray(A.cpu() if isinstance(A, torch.Tensor) else A)

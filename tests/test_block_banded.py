@@ -95,3 +95,25 @@ def test_gpu_bbb_bitexact(pkg, oracle, fdtype):
     B2 = _bbb(pkg, g, dev)
     pkg.finite_difference_jacobian_(B2, f, x, fdtype, colorvec=colors)
     assert np.array_equal(B2.data.cpu().numpy()[touched], ref[touched])
+
+
+def test_block_banded_dense_blocks_structure(pkg, oracle):
+    # BlockBandedMatrix hook (ext/FiniteDiffBlockBandedMatricesExt.jl:44-68): every row of every in-band block
+    g = 6
+    n = g * g
+    B = pkg.BlockBandedMatrix([g] * g, [g] * g, (1, 1), data=torch.zeros((3 * (2 * (g - 1) + 1)) * n, dtype=torch.float64))
+    rows, cols, slots = B.findstructralnz()
+    S = np.zeros((n, n), bool)
+    S[rows - 1, cols - 1] = True
+    bi = np.arange(n) // g
+    assert np.array_equal(S, np.abs(np.subtract.outer(bi, bi)) <= 1)           # block tridiagonal, dense blocks
+    assert len(np.unique(slots)) == len(slots) and slots.max() <= B.w * n
+    colors = B.matrix_colors()
+    x = np.random.default_rng(2).random(n)
+    data = np.zeros(B.w * n)
+    oracle.jacobian(oracle.Problem.coo_to_slots(n, n, rows, cols, slots, B.w * n), data, f_lap5(g), x.copy(), colorvec=colors)
+    Jb = np.zeros((n, n))
+    Jb[rows - 1, cols - 1] = data[slots - 1]
+    Jd = np.zeros(n * n)
+    oracle.jacobian(oracle.Problem.dense(n, n), Jd, f_lap5(g), x.copy())
+    np.testing.assert_allclose(Jb, Jd.reshape(n, n, order="F"), rtol=1e-6, atol=1e-6)   # Jbb ≈ Jsparse (coloring_tests.jl:119)
