@@ -1013,6 +1013,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     if (P->sp_kind == SP_CSC && P->strategy == 1) return scatter_lists(g, l0, G);
     if (P->sp_kind == SP_BANDED) {
       BandArgs a{};
+      ScatterTimer tm(P, s);   // one timed region per group: the pre-division pass (when used) + the band kernel
       a.jcolor = P->jcolor; a.fx = vfx; a.Fp = P->Fp; a.Fm = P->Fm; a.eps = P->eps; a.local_of = P->local_of;
       a.J = J; a.C = P->C; a.l0 = (int32_t)l0; a.G = (int32_t)G;
       a.write_other = (g == 0 && P->rank == 0) ? 1 : 0;
@@ -1022,17 +1023,43 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       int64_t ntiles;
       a.cols_per_tile = std::max<int64_t>(1, 4096 / w);
       ntiles = (P->n + a.cols_per_tile - 1) / a.cols_per_tile;
+      // every (colour, row) quotient lands in about (l+u+1)/C columns of the whole-band fill: when that reuse is >= 2,
+      // divide once per (colour, row) in place (the reference's own `vfx1 = (vfx1 - vfx)/eps` pass) and let the band
+      // kernel copy; otherwise divide at gather time.
+      // r1 measurements on C3 (16 GB band, 5 colours; scatter ms per Jacobian): warp-per-column 3.60, flat stream
+      // dividing at gather time 4.76, flat stream over pre-divided slabs 3.19, the same with 4-deep batched loads 3.04
+      // (kept); row-stationary 3.58, colour-grouped columns 3.46 and block-per-column 4.06 were tried and dropped.
+      const bool prediv = !COMPLEX && w >= 64 && P->n > 0 && P->C > 0 && G > 0 && w >= 2 * (int64_t)P->C;
+      if (prediv) {
+        dim3 grid((unsigned)std::max(1, std::min(P->grid(P->m), std::max(1, P->sm_count * 8 / (int)G))), (unsigned)G);
+        diff_slabs<MODE><<<grid, kThreads, 0, s>>>(P->Fp, CENTRAL ? P->Fm : vfx, P->eps, P->d_local_colors + l0, P->m, sF);
+        P->cnt.kernel_launches += 1;
+      }
       if (w >= 64 && P->n > 0) {
         // wide band: one warp per column
         const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
-        const int grid = resident_grid(P, diff_scatter_band_wide<CT, MODE>, sm, (P->n + 7) / 8);
-        ScatterTimer tm(P, s);
-        diff_scatter_band_wide<CT, MODE><<<grid, kThreads, sm, s>>>(a);
+        if (!a.to_dense && (reinterpret_cast<uintptr_t>(J) & 15) == 0) {
+          // band-data target: aligned flat stream, 16-byte stores
+          const int32_t CH = (int32_t)std::min<int64_t>(2048, w & ~(int64_t)1);
+          const int64_t nchunks = (w * P->n + CH - 1) / CH;
+          if (prediv) {
+            const int grid = resident_grid(P, diff_scatter_band_flat<CT, kCopy>, sm, (nchunks + 7) / 8);
+            diff_scatter_band_flat<CT, kCopy><<<grid, kThreads, sm, s>>>(a, CH);
+          } else {
+            const int grid = resident_grid(P, diff_scatter_band_flat<CT, MODE>, sm, (nchunks + 7) / 8);
+            diff_scatter_band_flat<CT, MODE><<<grid, kThreads, sm, s>>>(a, CH);
+          }
+        } else if (prediv) {
+          const int grid = resident_grid(P, diff_scatter_band_wide<CT, kCopy>, sm, (P->n + 7) / 8);
+          diff_scatter_band_wide<CT, kCopy><<<grid, kThreads, sm, s>>>(a);
+        } else {
+          const int grid = resident_grid(P, diff_scatter_band_wide<CT, MODE>, sm, (P->n + 7) / 8);
+          diff_scatter_band_wide<CT, MODE><<<grid, kThreads, sm, s>>>(a);
+        }
         P->cnt.kernel_launches += 1;
         P->cnt.scatter_launches += 1;
       } else if (ntiles > 0) {
         const int blocks = (int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16);
-        ScatterTimer tm(P, s);
         diff_scatter_band<CT, MODE><<<blocks, kThreads, 0, s>>>(a);
         P->cnt.kernel_launches += 1;
         P->cnt.scatter_launches += 1;

@@ -36,8 +36,11 @@ __device__ __forceinline__ double eps_from_sumsq(double ss, const EpsParams &p) 
 template <int NC>
 __device__ __forceinline__ void sumsq_accumulate(double (&acc)[NC], double v, uint32_t c) {
   const double sq = v * v;
+  // predicated adds (ISETP + @P DADD): an element belongs to exactly one colour, the other accumulators are untouched
+  // — same values as adding 0.0, half the instructions of a select+add (the r1 capture showed this kernel issue-bound)
 #pragma unroll
-  for (int k = 0; k < NC; ++k) acc[k] += (c == (uint32_t)k) ? sq : 0.0;
+  for (int k = 0; k < NC; ++k)
+    if (c == (uint32_t)k) acc[k] += sq;
 }
 
 template <typename CT, int NC>

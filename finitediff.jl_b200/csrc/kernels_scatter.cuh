@@ -20,13 +20,14 @@
 namespace fdb {
 
 // finite-difference flavour of a kernel instantiation
-enum : int { kForward = 0, kCentral = 1, kComplex = 2 };
+enum : int { kForward = 0, kCentral = 1, kComplex = 2, kCopy = 3 /* slab already holds the quotients */ };
 
 // The quotient the reference stores.  `hi` = the colour's slab (f(x+eps e_k); complex step: complex128 interleaved,
 // so the imaginary part of row r sits at 2r+1 and ldF counts doubles), `lo` = f(x) (forward) / the minus slab (central).
 template <int MODE>
 __device__ __forceinline__ double fd_quotient(const double *__restrict__ hi, const double *__restrict__ lo, int64_t r,
                                               double e) {
+  if (MODE == kCopy) return __ldg(hi + r);                           // quotient precomputed in place (diff_slabs)
   if (MODE == kComplex) return __ldg(hi + 2 * r + 1) / e;            // jacobians.jl:636  imag(vfx) / epsilon
   const double d = __ldg(hi + r) - __ldg(lo + r);
   return d / (MODE == kCentral ? 2 * e : e);                         // :565 (vfx1-vfx)/epsilon ; :607 .../2epsilon
@@ -282,6 +283,23 @@ __device__ __forceinline__ void band_color_lookup(const BandArgs &a, uint32_t k,
   }
 }
 
+// The reference's own in-place pass `@. vfx1 = (vfx1 - vfx) / epsilon` (jacobians.jl:565 / :607), for the slabs of one
+// group.  Only used where a quotient is stored MANY times: the whole-band fill of an under-coloured banded sparsity
+// writes every (colour, row) value into (l+u+1)/C columns (C3: 400x) — dividing once per (colour, row) instead of once
+// per slot removes 2*10^9 fp64 divisions from the 16 GB store stream.  The scatter then runs in kCopy mode.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+diff_slabs(double *__restrict__ Fp, const double *__restrict__ Fm_or_fx, const double *__restrict__ eps,
+           const int32_t *__restrict__ slab_color /* global colour of each slab of the group */, int64_t m, int64_t ldF) {
+  const int s = blockIdx.y;
+  const double e = __ldg(eps + __ldg(slab_color + s));
+  const double denom = MODE == kCentral ? 2 * e : e;
+  double *__restrict__ hi = Fp + (int64_t)s * ldF;
+  const double *__restrict__ lo = MODE == kCentral ? Fm_or_fx + (int64_t)s * ldF : Fm_or_fx;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < m; r += stride) hi[r] = (hi[r] - lo[r]) / denom;
+}
+
 // Wide bands (l+u+1 >= 64): ONE WARP PER COLUMN.  A band column is a contiguous run of l+u+1 slots whose sources
 // F[slab][c-u .. c+l] are contiguous too; the warp walks it 32 slots at a time (256-byte coalesced stores, coalesced
 // L2-resident gathers).  The per-column work (colour -> slab, eps) is one uniform lookup from shared-memory tables,
@@ -337,6 +355,149 @@ diff_scatter_band_wide(const BandArgs a) {
         for (int d = d_lo + lane; d < d_hi; d += 32) st_stream(out + d, 0.0);
       }
       for (int d = d_hi + lane; d < wi; d += 32) st_stream(out + d, 0.0);
+    }
+  }
+}
+
+// Wide bands, band-data target, FLAT form: the (l+u+1) x n band storage is one contiguous stream (column c+1 starts
+// right after column c).  Each warp takes 16-byte-aligned chunks of that stream (CH elements, CH <= l+u+1 so a chunk
+// touches at most two columns) and writes them with fully aligned 16-byte stores — the warp-per-column form above
+// starts every column at an 8-byte-aligned, sector-straddling address (w odd) and reached only ~4.5 of the 7.5 TB/s
+// a pure store stream gets on this part (profiles/write_bw_probe.py).  One 64-bit division per chunk locates the column.
+struct BandColumn {
+  const double *hi, *lo;   // slab pointers already offset so that [d] addresses row c-u+d
+  double e;
+  int d_lo, d_hi;          // in-matrix slot range
+  bool owned, zero_col;
+};
+
+template <typename CT, int MODE>
+__device__ __forceinline__ BandColumn band_column(const BandArgs &a, const CT *__restrict__ jcolor, int64_t c, bool tables,
+                                                  const int32_t *s_slab, const double *s_eps, int64_t w) {
+  BandColumn b{};
+  if (c >= a.n) return b;
+  const uint32_t k = (uint32_t)jcolor[c];
+  int32_t slab;
+  band_color_lookup(a, k, tables, s_slab, s_eps, slab, b.e);
+  b.owned = slab >= 0;
+  b.zero_col = k >= (uint32_t)a.C && a.write_other;
+  const int64_t r0 = c - a.u;
+  b.hi = a.Fp + (int64_t)(b.owned ? slab : 0) * a.ldF + (MODE == kComplex ? 2 * r0 : r0);
+  b.lo = (MODE == kCentral ? a.Fm + (int64_t)(b.owned ? slab : 0) * a.ldF : a.fx) + r0;
+  const int64_t lo64 = -r0 > 0 ? -r0 : 0;
+  const int64_t hi64 = a.m - r0 < w ? a.m - r0 : w;
+  b.d_lo = (int)lo64;
+  b.d_hi = (int)(hi64 > lo64 ? hi64 : lo64);
+  return b;
+}
+
+template <int MODE>
+__device__ __forceinline__ double band_value(const BandColumn &b, int d) {
+  if (!b.owned || d < b.d_lo || d >= b.d_hi) return 0.0;          // corner slots / columns without a valid colour: 0
+  if (MODE == kComplex) return __ldg(b.hi + 2 * d + 1) / b.e;
+  if (MODE == kCopy) return __ldg(b.hi + d);
+  const double df = __ldg(b.hi + d) - __ldg(b.lo + d);
+  return df / (MODE == kCentral ? 2 * b.e : b.e);
+}
+
+// Interior stretch of a band column in copy mode: out[off] = src[off] for the even-aligned pairs of [s, e).  The
+// sources are only 8-byte aligned relative to the destination, so they come as scalar L2 loads; kBandBatch pairs are
+// loaded before the first store so that each lane keeps 64 bytes of loads in flight (the kernel is latency-bound
+// otherwise: ncu showed ~60% of DRAM write bandwidth with every warp stalled on its one outstanding load pair).
+constexpr int kBandBatch = 4;
+__device__ __forceinline__ void band_copy_run(double *__restrict__ out, const double *__restrict__ src, int s, int e,
+                                              int lane) {
+  int off = s + 2 * lane;
+  for (; off + 64 * (kBandBatch - 1) < e; off += 64 * kBandBatch) {
+    double v[2 * kBandBatch];
+#pragma unroll
+    for (int u = 0; u < kBandBatch; ++u) {
+      v[2 * u] = __ldg(src + off + 64 * u);
+      v[2 * u + 1] = __ldg(src + off + 64 * u + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < kBandBatch; ++u) st_stream2(out + off + 64 * u, v[2 * u], v[2 * u + 1]);
+  }
+  for (; off < e; off += 64) st_stream2(out + off, __ldg(src + off), __ldg(src + off + 1));
+}
+
+template <typename CT, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+diff_scatter_band_flat(const BandArgs a, int32_t CH /* elements per chunk: even, <= l+u+1 */) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double *s_eps = reinterpret_cast<double *>(smem);
+  int32_t *s_slab = reinterpret_cast<int32_t *>(smem + sizeof(double) * (a.C <= kSmemTable ? a.C : 0));
+  const bool tables = a.C <= kSmemTable;
+  if (tables) {
+    for (int i = threadIdx.x; i < a.C; i += kThreads) {
+      const int32_t lo = a.local_of[i];
+      int32_t sl = lo < 0 ? -1 : lo - a.l0;
+      if (sl >= a.G) sl = -1;
+      s_slab[i] = sl;
+      s_eps[i] = a.eps[i];
+    }
+    __syncthreads();
+  }
+  const CT *__restrict__ jcolor = reinterpret_cast<const CT *>(a.jcolor);
+  const int lane = threadIdx.x & 31;
+  const int64_t w = a.l + a.u + 1;
+  const int wi = (int)w;
+  const int64_t total = w * a.n;
+  const int64_t nchunks = (total + CH - 1) / CH;
+  const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t ch = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); ch < nchunks; ch += nwarps) {
+    const int64_t q0 = ch * CH;
+    const int64_t c0 = q0 / w;
+    const int d0 = (int)(q0 - c0 * w);
+    const BandColumn A = band_column<CT, MODE>(a, jcolor, c0, tables, s_slab, s_eps, w);
+    const BandColumn B = band_column<CT, MODE>(a, jcolor, c0 + 1, tables, s_slab, s_eps, w);
+    const bool wA = A.owned || A.zero_col, wB = B.owned || B.zero_col;   // columns this launch defines
+    int64_t lim = total - q0;
+    if (lim > CH) lim = CH;
+    double *__restrict__ out = a.J + q0;
+    const int ilim = (int)lim;
+    // generic pair loop over offsets [s, e): per-element column select, range tests, ownership
+    auto generic = [&](int s, int e) {
+      for (int off = s + 2 * lane; off < e; off += 64) {
+        const int da = d0 + off, db = d0 + off + 1;
+        const bool a_in_A = da < wi, b_in_A = db < wi;
+        const double v0 = a_in_A ? band_value<MODE>(A, da) : band_value<MODE>(B, da - wi);
+        const bool w0 = a_in_A ? wA : wB;
+        if (off + 1 < e) {
+          const double v1 = b_in_A ? band_value<MODE>(A, db) : band_value<MODE>(B, db - wi);
+          const bool w1 = b_in_A ? wA : wB;
+          if (w0 && w1) st_stream2(out + off, v0, v1);
+          else { if (w0) out[off] = v0; if (w1) out[off + 1] = v1; }
+        } else if (w0) {
+          out[off] = v0;
+        }
+      }
+    };
+    if (MODE == kCopy) {
+      // copy mode: the chunk is [0,nA) of column A then [nA,lim) of column B; interior stretches (owned column, all
+      // slots inside the matrix) are plain aligned-store copies with no per-element tests: loads batch 4 deep
+      const int nA = wi - d0 < ilim ? wi - d0 : ilim;
+      const int nAe = nA & ~1;                           // even part of A; an odd nA leaves one straddling pair
+      const int sB = (nA & 1) ? nA + 1 : nA;
+      const int eB = ilim & ~1;
+      const bool fastA = A.owned && d0 >= A.d_lo && d0 + nAe <= A.d_hi;
+      const bool fastB = B.owned && sB < eB && (sB - nA) >= B.d_lo && (eB - nA) <= B.d_hi;
+      if (fastA) {
+        const double *__restrict__ src = A.hi + d0;
+        band_copy_run(out, src, 0, nAe, lane);
+      } else {
+        generic(0, nAe);
+      }
+      if (nA & 1) generic(nAe, nAe + 2 < ilim ? nAe + 2 : ilim);
+      if (fastB) {
+        const double *__restrict__ src = B.hi - nA;        // slot d of B sits at offset nA + d
+        band_copy_run(out, src, sB, eB, lane);
+        if (eB < ilim) generic(eB, ilim);
+      } else if (sB < ilim) {
+        generic(sB, ilim);
+      }
+    } else {
+      generic(0, ilim);
     }
   }
 }

@@ -1,0 +1,19 @@
+"""Pure-write HBM bandwidth probe (what a store-only kernel such as the banded whole-band fill can reach):
+torch fill_ and cudaMemsetAsync over 16 GB, CUDA-event timed, best of 5."""
+import torch
+n = 2_000_000_000
+t = torch.empty(n, dtype=torch.float64, device="cuda")
+for name, fn in (("fill_", lambda: t.fill_(1.0)), ("zero_", lambda: t.zero_())):
+    best = 1e9
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b))
+    print(name, f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s")
+src = torch.empty(n // 2, dtype=torch.float64, device="cuda"); dst = torch.empty_like(src)
+best = 1e9
+for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); dst.copy_(src); b.record(); torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+print("copy_", f"{best:.3f} ms  {2*src.numel()*8/best/1e6:.1f} GB/s (read+write)")
