@@ -104,6 +104,7 @@ struct fdb_plan {
   double *eps = nullptr, *sumsq = nullptr, *partial = nullptr;
   int eps_blocks = 0;
   int64_t eps_chunk = 0;
+  int32_t eps_group = 1;   // largest aligned lane group without a repeated colour (color_lane_conflicts)
   unsigned int *ticket = nullptr;   // last-block-done counter of color_sumsq_reg
   bool peers_aligned = true;
   // scratch
@@ -245,12 +246,28 @@ static fdb_status setup_colors(fdb_plan *P, const int64_t *colorvec /*host or de
   P->color_bits = mx <= 255 ? 8 : (mx <= 65535 ? 16 : 32);
   TRY(P->alloc(&P->jcolor, (size_t)std::max<int64_t>(n, 1) * (P->color_bits / 8)));
   if (n > 0) {
-    TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+    uint32_t *d_flags = nullptr;
+    const bool window_path = P->C > kEpsRegColors;
+    if (window_path) {
+      CU(cudaMalloc((void **)&d_flags, sizeof(uint32_t)));
+      CU(cudaMemset(d_flags, 0, sizeof(uint32_t)));
+    }
+    fdb_status st = dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
       using CT = decltype(tag);
       convert_colors<CT><<<P->grid(n), kThreads>>>(cv.d, n, (CT *)P->jcolor);
+      if (window_path) color_lane_conflicts<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, n, P->C, d_flags);
       CU(cudaGetLastError());
       return FDB_OK;
-    }));
+    });
+    if (st == FDB_OK && window_path) {
+      uint32_t flags = 0;
+      cudaError_t e = cudaMemcpy(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) st = fail(FDB_ERR_CUDA, "colour conflict flags: %s", cudaGetErrorString(e));
+      P->eps_group = 1;
+      for (int lg = 1; lg <= 5 && !(flags & (1u << lg)); ++lg) P->eps_group = 1 << lg;
+    }
+    if (d_flags) cudaFree(d_flags);
+    if (st != FDB_OK) return st;
   }
   return FDB_OK;
 }
@@ -292,11 +309,11 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   TRY(P->alloc_t(&P->sumsq, std::max<int32_t>(C, 1)));
   {
     int64_t nb = (P->n + 2047) / 2048;
-    // window path: 32 KB of shared memory per block -> keep the grid within one resident wave
-    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * (C <= kEpsRegColors ? 8 : 4)));
+    // window path: 64 bytes of shared memory per window colour and block (<= 32 KB) -> one resident wave
+    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * (C <= 256 ? 8 : 6)));
     P->eps_blocks = (int)nb;
     int64_t chunk = (P->n + nb - 1) / nb;
-    P->eps_chunk = std::max<int64_t>(chunk, 1);
+    P->eps_chunk = (std::max<int64_t>(chunk, 1) + 31) & ~(int64_t)31;   // aligned 32-column steps on the window path
     const int64_t stride = C <= kEpsRegColors ? kEpsRegColors : std::min<int64_t>(C, kEpsWindow);
     TRY(P->alloc_t(&P->partial, (size_t)nb * stride));
     TRY(P->alloc_t(&P->ticket, 4));
@@ -507,7 +524,8 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
   if (nnz > 0) {
     PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
       using CT = decltype(tag);
-      expand_csc<CT><<<P->grid(nnz), kThreads>>>(cp.d, rv.d, m, n, nnz, (const CT *)P->jcolor, P->C, P->row32,
+      const size_t hsm = P->C <= kPlanSmemColors ? (size_t)std::max<int32_t>(P->C, 1) * sizeof(unsigned int) : 0;
+      expand_csc<CT><<<P->grid(nnz), kThreads, hsm>>>(cp.d, rv.d, m, n, nnz, (const CT *)P->jcolor, P->C, P->row32,
                                                  (CT *)P->ecolor, col32, d_cnt, d_err);
       CU(cudaGetLastError());
       return FDB_OK;
@@ -620,7 +638,8 @@ fdb_status fdb_plan_create_coo(fdb_plan **plan, int64_t m, int64_t n, int64_t nn
   if (nnz > 0) {
     PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
       using CT = decltype(tag);
-      prepare_coo<CT><<<P->grid(nnz), kThreads>>>(rv.d, cvw.d, jkind == FDB_J_SLOTS ? sv.d : nullptr, nnz, m, n, P->ldJ,
+      const size_t hsm = P->C <= kPlanSmemColors ? (size_t)std::max<int32_t>(P->C, 1) * sizeof(unsigned int) : 0;
+      prepare_coo<CT><<<P->grid(nnz), kThreads, hsm>>>(rv.d, cvw.d, jkind == FDB_J_SLOTS ? sv.d : nullptr, nnz, m, n, P->ldJ,
                                                   P->j_len, (const CT *)P->jcolor, P->C, P->row32, (CT *)P->ecolor,
                                                   P->dest, d_cnt, d_err);
       CU(cudaGetLastError());
@@ -895,7 +914,7 @@ static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double a
     for (int32_t k0 = 0; k0 < C; k0 += kEpsWindow) {
       const int32_t W = std::min<int32_t>(kEpsWindow, C - k0);
       color_sumsq_win<CT><<<P->eps_blocks, kThreads, (size_t)kEpsWarps * W * sizeof(double), s>>>(
-          x, (const CT *)P->jcolor, P->n, P->eps_chunk, k0, W, P->partial);
+          x, (const CT *)P->jcolor, P->n, P->eps_chunk, k0, W, P->eps_group, P->partial);
       // partial rows are W wide for this pass
       finalize_eps<<<(W * 32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(P->partial, P->eps_blocks, W, k0, W, prm,
                                                                         P->eps, P->sumsq);

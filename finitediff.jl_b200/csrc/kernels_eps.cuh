@@ -15,6 +15,7 @@ namespace fdb {
 constexpr int kEpsRegColors = 8;     // register path when C <= 8
 constexpr int kEpsWindow = 512;      // colours per pass on the shared-memory path
 constexpr int kEpsWarps = kThreads / 32;
+constexpr int kEpsBatch = 4;        // 32-wide steps whose loads are in flight together on the window path
 
 struct EpsParams {
   int fdtype_central;
@@ -122,44 +123,69 @@ color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int
   if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next call (stream-ordered)
 }
 
-// General C: colours [k0, k0+W) per pass; every warp owns a private W-entry accumulator in shared memory, lanes that
-// hold the same colour are combined in ascending lane order (match.any), the lowest lane adds into the warp's slot.
+// General C: colours [k0, k0+W) per pass; every warp owns a private W-entry accumulator in shared memory and walks
+// the block's range in aligned 32-column steps.  `group` (plan time, color_lane_conflicts) is the largest lane-group
+// size whose aligned groups never repeat a colour: the 32/group groups of a step update the accumulators one after the
+// other, lanes of a group all at once — plain shared-memory read-modify-writes, no collectives (r1: the match.any
+// version was bound by the MIO queue, 0.5-1 TB/s).  group < 4 (arbitrary colourings) falls back to combining equal
+// colours with match.any in ascending lane order.  Accumulation order is fixed either way.
 template <typename CT>
 __global__ void __launch_bounds__(kThreads)
 color_sumsq_win(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int64_t chunk, int32_t k0,
-                int32_t W, double *__restrict__ partial /* [gridDim.x][W] */) {
+                int32_t W, int32_t group, double *__restrict__ partial /* [gridDim.x][W] */) {
   extern __shared__ double sacc[];  // kEpsWarps * W
   for (int i = threadIdx.x; i < kEpsWarps * W; i += kThreads) sacc[i] = 0.0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double *acc = sacc + (size_t)w * W;
-  const int64_t start = (int64_t)blockIdx.x * chunk;
+  const int64_t start = (int64_t)blockIdx.x * chunk;     // chunk is a multiple of 32: steps are aligned column groups
   int64_t end = start + chunk;
   if (end > n) end = n;
-  // warp w walks the block's range in 32-wide steps: step t covers [start + (t*kEpsWarps + w)*32, +32)
-  for (int64_t base = start + (int64_t)w * 32; base < end; base += (int64_t)kEpsWarps * 32) {
-    const int64_t j = base + lane;
-    int32_t c = -1;
-    double sq = 0.0;
-    if (j < end) {
-      const double v = x[j];
-      sq = v * v;
-      const int32_t cc = (int32_t)(uint32_t)jcolor[j] - k0;
-      if (cc >= 0 && cc < W) c = cc;
-    }
-    const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-    if (c >= 0) {
-      const unsigned peers = __match_any_sync(act, c);
-      double s = 0.0;
-      unsigned mm = peers;
-      while (mm) {
-        const int l = __ffs(mm) - 1;
-        mm &= mm - 1;
-        s += __shfl_sync(peers, sq, l);
+  // warp w takes the steps [start + (t*kEpsWarps + w)*32, +32); the loads of kEpsBatch steps are issued before the
+  // first one is accumulated
+  constexpr int64_t kStep = (int64_t)kEpsWarps * 32;
+  const int my_group = lane / (group > 0 ? group : 1);
+  for (int64_t base = start + (int64_t)w * 32; base < end; base += kStep * kEpsBatch) {
+    double v[kEpsBatch];
+    int32_t cc[kEpsBatch];
+#pragma unroll
+    for (int u = 0; u < kEpsBatch; ++u) {
+      const int64_t j = base + u * kStep + lane;
+      v[u] = 0.0;
+      cc[u] = -1;
+      if (j < end) {
+        v[u] = ld_stream(x + j);
+        cc[u] = (int32_t)(uint32_t)jcolor[j] - k0;
       }
-      if (lane == __ffs(peers) - 1) acc[c] += s;
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kEpsBatch; ++u) {
+      const int32_t c = (cc[u] >= 0 && cc[u] < W) ? cc[u] : -1;
+      const double sq = v[u] * v[u];
+      if (group == 32) {
+        if (c >= 0) acc[c] += sq;
+        __syncwarp();
+      } else if (group >= 4) {
+        for (int ph = 0; ph < 32 / group; ++ph) {
+          if (c >= 0 && my_group == ph) acc[c] += sq;
+          __syncwarp();
+        }
+      } else {
+        const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+        if (c >= 0) {
+          const unsigned peers = __match_any_sync(act, c);
+          double s = 0.0;
+          unsigned mm = peers;
+          while (mm) {
+            const int l = __ffs(mm) - 1;
+            mm &= mm - 1;
+            s += __shfl_sync(peers, sq, l);
+          }
+          if (lane == __ffs(peers) - 1) acc[c] += s;
+        }
+        __syncwarp();
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W; i += kThreads) {

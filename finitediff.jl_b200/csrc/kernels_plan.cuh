@@ -74,25 +74,63 @@ __device__ __forceinline__ int64_t csc_col_of(const int64_t *__restrict__ colptr
   return lo;
 }
 
-// For every CSC slot p: row32[p], ecolor[p] (colour of its column), optional col32[p]; per-colour entry counts.
+// Per-colour counting shared by the plan kernels: lanes of a warp holding the same colour are combined (match.any),
+// the group's leader adds the population to the block's shared-memory histogram (C <= kPlanSmemColors) or straight
+// to the global counters.  Must be reached by all 32 lanes of the warp (`k` >= C for lanes with nothing to count).
+constexpr int kPlanSmemColors = 4096;
+__device__ __forceinline__ void count_color(uint32_t k, int32_t C, unsigned int *s_cnt /* null => global */,
+                                            unsigned long long *__restrict__ color_count) {
+  const bool valid = k < (uint32_t)C;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const unsigned peers = __match_any_sync(act, k);
+  if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
+  if (s_cnt) atomicAdd(s_cnt + k, (unsigned int)__popc(peers));
+  else atomicAdd(color_count + k, (unsigned long long)__popc(peers));
+}
+__device__ __forceinline__ unsigned int *count_begin(unsigned int *smem, int32_t C, const unsigned long long *color_count) {
+  if (color_count == nullptr || C > kPlanSmemColors) return nullptr;
+  for (int i = threadIdx.x; i < C; i += kThreads) smem[i] = 0u;
+  __syncthreads();
+  return smem;
+}
+__device__ __forceinline__ void count_end(unsigned int *s_cnt, int32_t C, unsigned long long *__restrict__ color_count) {
+  if (!s_cnt) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += kThreads)
+    if (s_cnt[i]) atomicAdd(color_count + i, (unsigned long long)s_cnt[i]);
+}
+
+// For every CSC slot p: row32[p], ecolor[p] (colour of its column), optional col32[p]; per-colour entry counts
+// (r1's one-global-atomic-per-entry version serialised 3*10^7 atomics on 3 addresses: 7.6 ms of the C2 plan build).
 template <typename CT>
 __global__ void __launch_bounds__(kThreads)
 expand_csc(const int64_t *__restrict__ colptr, const int64_t *__restrict__ rowval, int64_t m, int64_t n, int64_t nnz,
            const CT *__restrict__ jcolor, int32_t C, int32_t *__restrict__ row32, CT *__restrict__ ecolor,
            int32_t *__restrict__ col32 /* nullable */, unsigned long long *__restrict__ color_count /* [C] nullable */,
            uint32_t *__restrict__ err) {
+  extern __shared__ unsigned int s_hist[];   // [C] when C <= kPlanSmemColors and counts are wanted
+  unsigned int *s_cnt = count_begin(s_hist, C, color_count);
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < nnz; p += stride) {
-    const int64_t c = csc_col_of(colptr, n, p);
-    const int64_t r = rowval[p];
-    if (r < 1 || r > m) { atomicOr(err, kErrRowRange); row32[p] = 0; }
-    else row32[p] = (int32_t)(r - 1);
-    if (p > colptr[c] - 1 && rowval[p - 1] >= r) atomicOr(err, kErrRowOrder);
-    const CT k = jcolor[c];
-    ecolor[p] = k;
-    if (col32) col32[p] = (int32_t)c;
-    if (color_count && (uint32_t)k < (uint32_t)C) atomicAdd(color_count + (uint32_t)k, 1ull);
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: count_color uses full-warp collectives
+  for (int64_t p0 = blockIdx.x * (int64_t)kThreads + threadIdx.x - lane; p0 < nnz; p0 += stride) {
+    const int64_t p = p0 + lane;
+    uint32_t k = 0xffffffffu;
+    if (p < nnz) {
+      const int64_t c = csc_col_of(colptr, n, p);
+      const int64_t r = rowval[p];
+      if (r < 1 || r > m) { atomicOr(err, kErrRowRange); row32[p] = 0; }
+      else row32[p] = (int32_t)(r - 1);
+      if (p > colptr[c] - 1 && rowval[p - 1] >= r) atomicOr(err, kErrRowOrder);
+      const CT kc = jcolor[c];
+      ecolor[p] = kc;
+      if (col32) col32[p] = (int32_t)c;
+      k = (uint32_t)kc;
+    }
+    if (color_count) count_color(k, C, s_cnt, color_count);
   }
+  count_end(s_cnt, C, color_count);
 }
 
 // same-pattern test of ext/FiniteDiffSparseArraysExt.jl:51-52:  J.colptr == sp.colptr && J.rowval == sp.rowval
@@ -141,24 +179,33 @@ prepare_coo(const int64_t *__restrict__ rows, const int64_t *__restrict__ cols, 
             int64_t nnz, int64_t m, int64_t n, int64_t ldJ, int64_t j_len, const CT *__restrict__ jcolor, int32_t C,
             int32_t *__restrict__ row32, CT *__restrict__ ecolor, int64_t *__restrict__ dest,
             unsigned long long *__restrict__ color_count, uint32_t *__restrict__ err) {
+  extern __shared__ unsigned int s_hist[];
+  unsigned int *s_cnt = count_begin(s_hist, C, color_count);
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t e = blockIdx.x * (int64_t)kThreads + threadIdx.x; e < nnz; e += stride) {
-    int64_t r = rows[e], c = cols[e];
-    if (r < 1 || r > m) { atomicOr(err, kErrRowRange); r = 1; }
-    if (c < 1 || c > n) { atomicOr(err, kErrColRange); c = 1; }
-    row32[e] = (int32_t)(r - 1);
-    const CT k = jcolor[c - 1];
-    ecolor[e] = k;
-    int64_t d;
-    if (slots) {
-      d = slots[e] - 1;
-      if (d < 0 || d >= j_len) { atomicOr(err, kErrSlotRange); d = 0; }
-    } else {
-      d = (c - 1) * ldJ + (r - 1);
+  const int lane = threadIdx.x & 31;
+  for (int64_t e0 = blockIdx.x * (int64_t)kThreads + threadIdx.x - lane; e0 < nnz; e0 += stride) {
+    const int64_t e = e0 + lane;
+    uint32_t kk = 0xffffffffu;
+    if (e < nnz) {
+      int64_t r = rows[e], c = cols[e];
+      if (r < 1 || r > m) { atomicOr(err, kErrRowRange); r = 1; }
+      if (c < 1 || c > n) { atomicOr(err, kErrColRange); c = 1; }
+      row32[e] = (int32_t)(r - 1);
+      const CT k = jcolor[c - 1];
+      ecolor[e] = k;
+      int64_t d;
+      if (slots) {
+        d = slots[e] - 1;
+        if (d < 0 || d >= j_len) { atomicOr(err, kErrSlotRange); d = 0; }
+      } else {
+        d = (c - 1) * ldJ + (r - 1);
+      }
+      dest[e] = d;
+      kk = (uint32_t)k;
     }
-    dest[e] = d;
-    if (color_count && (uint32_t)k < (uint32_t)C) atomicAdd(color_count + (uint32_t)k, 1ull);
+    if (color_count) count_color(kk, C, s_cnt, color_count);
   }
+  count_end(s_cnt, C, color_count);
 }
 
 // ---- per-colour column lists (the reference's "for col in 1:ncols; if colorvec[col]==color_i" test, done ONCE) ----
@@ -207,6 +254,33 @@ bucket_columns(const CT *__restrict__ jcolor, int64_t n, int32_t C, unsigned lon
       cols_by_color[base + rank] = (int32_t)c;
     }
   }
+}
+
+// Step-size plan aid: in which aligned lane groups of g = 2,4,8,16,32 consecutive columns does a colour repeat?
+// bit log2(g) of *flags is set when some aligned g-group holds two columns of the same valid colour.  The window
+// sum-of-squares kernel lets the lanes of a conflict-free group update their shared-memory accumulators without any
+// matching (cyclic / banded colourings with C >= 32 are conflict-free at g = 32).
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+color_lane_conflicts(const CT *__restrict__ jcolor, int64_t n, int32_t C, uint32_t *__restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int lane = threadIdx.x & 31;
+  uint32_t bad = 0;
+  for (int64_t c0 = blockIdx.x * (int64_t)kThreads + threadIdx.x - lane; c0 < n; c0 += stride) {
+    const int64_t c = c0 + lane;
+    const uint32_t k = c < n ? (uint32_t)jcolor[c] : 0xffffffffu;
+    const bool valid = k < (uint32_t)C;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const unsigned others = __match_any_sync(act, k) & ~(1u << lane);
+#pragma unroll
+    for (int lg = 1; lg <= 5; ++lg) {
+      const int g = 1 << lg;
+      const unsigned group = (g == 32 ? 0xffffffffu : ((1u << g) - 1u)) << (lane & ~(g - 1));
+      if (others & group) bad |= 1u << lg;
+    }
+  }
+  if (bad) atomicOr(flags, bad);
 }
 
 // gather-locality metric: sum over entries of min(|row[e+1]-row[e]|, 2^20) (decides fused single pass vs per-colour passes)

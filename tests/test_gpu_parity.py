@@ -721,3 +721,34 @@ def test_resize(pkg, dev):
     J = pkg.zeros_colmajor(6, 6, dev)
     pkg.finite_difference_jacobian_(J, lambda fx, xx: fx.copy_(xx * xx), x6, c)
     np.testing.assert_allclose(J.cpu().numpy(), np.diag(2 * x6.cpu().numpy()), atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["mod12", "mod20", "mod40", "random50", "random50_with_invalid"])
+def test_window_eps_lane_groups(pkg, oracle, dev, kind):
+    # C > 8 takes the shared-memory window reduction; the plan picks the widest conflict-free lane group
+    # (8 / 16 / 32 for cyclic colourings) or the match.any fallback (arbitrary colourings).  eps must agree with the
+    # reference formula (jacobians.jl:559-561) and J must be bit-identical to the oracle run with the device's eps.
+    n = 5003
+    colptr, rowval = tridiag_csc(n)
+    rng = np.random.default_rng(7)
+    if kind.startswith("mod"):
+        cv = (np.arange(n, dtype=np.int64) % int(kind[3:])) + 1
+    else:
+        cv = rng.integers(1, 51, n).astype(np.int64)
+        if kind.endswith("invalid"):
+            cv[rng.integers(0, n, 40)] = 0
+    x = dev_x(pkg, dev, n, 9)
+    xh = oracle.fill_x(n, 9)
+    J = pkg.SparseMatrixCSC(n, n, t64(colptr), t64(rowval), torch.full((len(rowval),), float("nan"), dtype=torch.float64, device=dev))
+    ctx = pkg._lib.TridiagCtx(n, 0)
+    cache = pkg.JacobianCache(x, "forward", colorvec=cv, sparsity=J, max_batch=16)
+    pkg.finite_difference_jacobian_(J, native(pkg, "fdbs_tridiag", ctx, 16), x, cache)
+    eps = cache._last_plan.eps()
+    C = int(cv.max())
+    rel = np.sqrt(np.finfo(float).eps)
+    ss = np.array([np.sum(xh[cv == k] ** 2) for k in range(1, C + 1)])
+    np.testing.assert_allclose(eps, np.maximum(rel * np.sqrt(np.sqrt(ss)), rel), rtol=1e-13)
+    ref = np.full(len(rowval), np.nan)
+    oracle.jacobian(oracle.Problem.csc_same(n, n, colptr, rowval), ref, oracle.native_fn("synth_tridiag"), xh.copy(),
+                    colorvec=cv, eps_override=eps, ctx=oracle.SynthTridiagCtx(n, 1))
+    assert np.array_equal(J.nzval.cpu().numpy(), ref)
