@@ -76,6 +76,9 @@ ABI_SYMBOLS = {
     "fdb_jacobian": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_jacobian_complex": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "fdb_jacobian_host": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64]),
+    "fdb_eps_plan_create": (_int, [_PP, _i64, _vp, C.POINTER(PlanOpts)]),
+    "fdb_color_eps": (_int, [_vp, _vp, _f64, _f64, _f64, _vp, _vp]),
+    "fdb_plan_set_external_eps": (_int, [_vp, _vp]),
     "fdb_jvp_plan_create": (_int, [_PP, _i64, _i64, C.POINTER(PlanOpts)]),
     "fdb_jvp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_host_alloc": (_int, [_PP, C.c_size_t]),
@@ -93,6 +96,7 @@ ABI_SYMBOLS = {
 SYNTH_SYMBOLS = {
     "fdbs_tridiag": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_tridiag_c": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "fdbs_tridiag_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_lap5": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_ellrows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "fdbs_rank1": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
@@ -104,6 +108,10 @@ SYNTH_SYMBOLS = {
 
 class TridiagCtx(C.Structure):
     _fields_ = [("n", _i64), ("calls", _i64)]
+
+
+class TridiagRowsCtx(C.Structure):
+    _fields_ = [("n", _i64), ("row0", _i64), ("nrows", _i64), ("x0", _i64), ("calls", _i64)]
 
 
 class Lap5Ctx(C.Structure):

@@ -52,7 +52,7 @@ static fdb_status fail(fdb_status st, const char *fmt, ...) {
     if (s__ != FDB_OK) return s__;   \
   } while (0)
 
-enum { SP_NONE = 0, SP_CSC = 1, SP_COO = 3, SP_BANDED = 4, SP_JVP = 5 };
+enum { SP_NONE = 0, SP_CSC = 1, SP_COO = 3, SP_BANDED = 4, SP_JVP = 5, SP_EPS = 6 };
 
 struct DeviceGuard {
   int prev = -1;
@@ -76,9 +76,11 @@ struct GraphKey {
   double relstep = 0, absstep = 0, dir = 0;
   int n_peers = 0;
   long long peer_generation = 0;
+  const void *ext_eps = nullptr;
   bool operator==(const GraphKey &o) const {
     return f == o.f && ctx == o.ctx && x == o.x && J == o.J && fx == o.fx && f_in == o.f_in && relstep == o.relstep &&
-           absstep == o.absstep && dir == o.dir && n_peers == o.n_peers && peer_generation == o.peer_generation;
+           absstep == o.absstep && dir == o.dir && n_peers == o.n_peers && peer_generation == o.peer_generation &&
+           ext_eps == o.ext_eps;
   }
 };
 
@@ -105,6 +107,7 @@ struct fdb_plan {
   int eps_blocks = 0;
   int64_t eps_chunk = 0;
   int32_t eps_group = 1;   // largest aligned lane group without a repeated colour (color_lane_conflicts)
+  const double *ext_eps = nullptr;   // step sizes supplied by the caller (fdb_plan_set_external_eps), device, >= C entries
   unsigned int *ticket = nullptr;   // last-block-done counter of color_sumsq_reg
   bool peers_aligned = true;
   // scratch
@@ -272,6 +275,27 @@ static fdb_status setup_colors(fdb_plan *P, const int64_t *colorvec /*host or de
   return FDB_OK;
 }
 
+// step-size buffers of a coloured plan: eps / sumsq per colour, block partials of the one-pass reduction
+static fdb_status alloc_eps_buffers(fdb_plan *P) {
+  const int32_t C = P->C;
+  TRY(P->alloc_t(&P->eps, std::max<int32_t>(C, 1)));
+  TRY(P->alloc_t(&P->sumsq, std::max<int32_t>(C, 1)));
+  {
+    int64_t nb = (P->n + 2047) / 2048;
+    // window path: 64 bytes of shared memory per window colour and block (<= 32 KB) -> one resident wave
+    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * (C <= 256 ? 8 : 6)));
+    P->eps_blocks = (int)nb;
+    int64_t chunk = (P->n + nb - 1) / nb;
+    P->eps_chunk = (std::max<int64_t>(chunk, 1) + 31) & ~(int64_t)31;   // aligned 32-column steps on the window path
+    const int64_t stride = C <= kEpsRegColors ? kEpsRegColors : std::min<int64_t>(C, kEpsWindow);
+    TRY(P->alloc_t(&P->partial, (size_t)nb * stride));
+    TRY(P->alloc_t(&P->ticket, 4));
+    CU(cudaMemset(P->ticket, 0, 16));
+  }
+
+  return FDB_OK;
+}
+
 // colour ownership (multi-GPU), local colour list, scratch sizing
 static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const std::vector<unsigned long long> &count) {
   const int32_t C = P->C;
@@ -304,21 +328,7 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   if (C > 0) CU(cudaMemcpy(P->local_of, local_of.data(), (size_t)C * 4, cudaMemcpyHostToDevice));
   if (n_local > 0) CU(cudaMemcpy(P->d_local_colors, P->local_colors.data(), (size_t)n_local * 4, cudaMemcpyHostToDevice));
 
-  // step-size buffers
-  TRY(P->alloc_t(&P->eps, std::max<int32_t>(C, 1)));
-  TRY(P->alloc_t(&P->sumsq, std::max<int32_t>(C, 1)));
-  {
-    int64_t nb = (P->n + 2047) / 2048;
-    // window path: 64 bytes of shared memory per window colour and block (<= 32 KB) -> one resident wave
-    nb = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)P->sm_count * (C <= 256 ? 8 : 6)));
-    P->eps_blocks = (int)nb;
-    int64_t chunk = (P->n + nb - 1) / nb;
-    P->eps_chunk = (std::max<int64_t>(chunk, 1) + 31) & ~(int64_t)31;   // aligned 32-column steps on the window path
-    const int64_t stride = C <= kEpsRegColors ? kEpsRegColors : std::min<int64_t>(C, kEpsWindow);
-    TRY(P->alloc_t(&P->partial, (size_t)nb * stride));
-    TRY(P->alloc_t(&P->ticket, 4));
-    CU(cudaMemset(P->ticket, 0, 16));
-  }
+  TRY(alloc_eps_buffers(P));
 
   // scratch: stacked f! outputs (slabs) + perturbed points
   const bool central = P->fdtype == FDB_CENTRAL;
@@ -941,7 +951,12 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   //  here would race with the peers' stores.
   const bool self_defining = (ident || band_data) && n_local > 0;
   if (!self_defining && P->n_peers == 0 && P->j_len > 0) CU(cudaMemsetAsync(J, 0, (size_t)P->j_len * 8, s));
-  TRY(run_eps<CT>(P, x, relstep, absstep, dir, s));
+  if (P->ext_eps) {
+    // sharded runs: the step sizes of the FULL x come from outside (fdb_color_eps on the full vector)
+    if (P->C > 0) CU(cudaMemcpyAsync(P->eps, P->ext_eps, (size_t)P->C * 8, cudaMemcpyDeviceToDevice, s));
+  } else {
+    TRY(run_eps<CT>(P, x, relstep, absstep, dir, s));
+  }
   const double *vfx = nullptr;
   if (MODE == kForward) {
     if (f_in) vfx = f_in;                                  // jacobians.jl:543-544
@@ -1229,6 +1244,7 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
   if (!P || !f) return fail(FDB_ERR_INVALID, "NULL plan or f");
   if ((P->n > 0 && !d_x) || (P->j_len > 0 && !d_J)) return fail(FDB_ERR_INVALID, "NULL x or J");
   if (P->sp_kind == SP_JVP) return fail(FDB_ERR_INVALID, "this is a JVP plan: call fdb_jvp");
+  if (P->sp_kind == SP_EPS) return fail(FDB_ERR_INVALID, "this is a step-size plan: call fdb_color_eps");
   if (P->fdtype == FDB_COMPLEX && !P->complex_entry)
     return fail(FDB_ERR_INVALID, "this plan is a complex-step plan: call fdb_jacobian_complex with a complex128 callback");
   DeviceGuard g(P->device);
@@ -1242,7 +1258,7 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
   if (P->use_graph && !P->timing) {
     // CUDA-graph replay of the whole call: the launch sequence depends only on the plan and on these arguments
     // (the step sizes are computed on the device inside the graph), so it is captured once and re-launched.
-    const GraphKey key{(void *)f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, P->n_peers, P->peer_generation};
+    const GraphKey key{(void *)f, ctx, d_x, d_J, fx, d_f_in, relstep, absstep, dir, P->n_peers, P->peer_generation, P->ext_eps};
     if (!P->graph_exec || !(key == P->graph_key)) {
       if (P->graph_exec) { cudaGraphExecDestroy(P->graph_exec); P->graph_exec = nullptr; }
       if (!P->cstream) CU(cudaStreamCreateWithFlags(&P->cstream, cudaStreamNonBlocking));
@@ -1289,6 +1305,47 @@ fdb_status fdb_jacobian_complex(fdb_plan *P, fdb_fn_c f, void *ctx, const double
   const fdb_status st = fdb_jacobian(P, reinterpret_cast<fdb_fn>(f), ctx, d_x, d_J, nullptr, nullptr, 0.0, 0.0, 1.0, stream);
   P->complex_entry = false;
   return st;
+}
+
+// ------------------------------------------------------------------------------------------------ step sizes on their own
+// (column-block sharded runs: every shard perturbs with the step sizes of the FULL x — jacobians.jl:559-561 takes the
+//  norm over all colour-k components)
+fdb_status fdb_eps_plan_create(fdb_plan **plan, int64_t n, const int64_t *colorvec, const fdb_plan_opts *opts) {
+  fdb_plan *P = nullptr;
+  TRY(new_plan(plan, opts, 0, n));
+  P = *plan;
+  DeviceGuard g(P->device);
+  P->sp_kind = SP_EPS;
+  I64View cv;
+  PLAN_TRY(setup_colors(P, colorvec, cv));
+  PLAN_TRY(alloc_eps_buffers(P));
+  return FDB_OK;
+}
+
+fdb_status fdb_color_eps(fdb_plan *P, const double *d_x, double relstep, double absstep, double dir, double *d_eps_out,
+                         void *stream) {
+  if (!P) return fail(FDB_ERR_INVALID, "NULL plan");
+  if (P->sp_kind == SP_NONE || P->sp_kind == SP_JVP) return fail(FDB_ERR_INVALID, "fdb_color_eps needs a coloured plan");
+  if (P->n > 0 && !d_x) return fail(FDB_ERR_INVALID, "NULL x");
+  DeviceGuard g(P->device);
+  if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);
+  if (!(absstep > 0)) absstep = relstep;
+  TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+    using CT = decltype(tag);
+    return run_eps<CT>(P, d_x, relstep, absstep, dir, s);
+  }));
+  if (d_eps_out && P->C > 0) CU(cudaMemcpyAsync(d_eps_out, P->eps, (size_t)P->C * 8, cudaMemcpyDeviceToDevice, s));
+  return FDB_OK;
+}
+
+fdb_status fdb_plan_set_external_eps(fdb_plan *P, const double *d_eps) {
+  if (!P) return fail(FDB_ERR_INVALID, "NULL plan");
+  if (P->sp_kind == SP_NONE || P->sp_kind == SP_JVP || P->sp_kind == SP_EPS)
+    return fail(FDB_ERR_INVALID, "external step sizes apply to coloured Jacobian plans");
+  P->ext_eps = d_eps;
+  return FDB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ JVP (src/jvp.jl:238-274)

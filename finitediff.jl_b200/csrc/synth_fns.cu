@@ -109,6 +109,24 @@ __global__ void __launch_bounds__(kT) k_rank1(double *__restrict__ fx, const dou
   }
 }
 
+// Slice-aware tridiagonal stencil (column-block sharded runs): rows [row0, row0+nrows) of the n-row problem, reading a
+// slice of x whose element 0 is global component x0.  Same expression per row as k_tridiag => bit-identical values.
+__global__ void __launch_bounds__(kT) k_tridiag_rows(double *__restrict__ fx, const double *__restrict__ x, int64_t n,
+                                                     int64_t row0, int64_t nrows, int64_t x0, int64_t ldfx, int64_t ldx) {
+  const double *xb = x + (int64_t)blockIdx.y * ldx - x0;     // xb[global index]
+  double *fb = fx + (int64_t)blockIdx.y * ldfx;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * kT) {
+    const int64_t r = row0 + i;
+    const double c = xb[r];
+    double o;
+    if (n == 1) o = mul(-2.0, c);
+    else if (r == 0) o = add(mul(-2.0, c), xb[1]);
+    else if (r == n - 1) o = sub(xb[r - 1], mul(2.0, c));
+    else o = add(sub(xb[r - 1], mul(2.0, c)), xb[r + 1]);
+    fb[i] = o;
+  }
+}
+
 // complex twin of k_tridiag (complex-step path): complex128 arrays as double2; the stencil on re and im separately
 __global__ void __launch_bounds__(kT) k_tridiag_c(double2 *__restrict__ fx, const double2 *__restrict__ x, int64_t n,
                                                   int64_t ldfx, int64_t ldx) {
@@ -164,6 +182,16 @@ int fdbs_tridiag(void *vctx, double *d_fx, const double *d_x, int64_t batch, int
   if (((uintptr_t)d_x & 15) || ((uintptr_t)d_fx & 15) || (ldx & 1) || (ldfx & 1)) return 2;
   dim3 grid((unsigned)blocks_for((c->n + 1) / 2), (unsigned)batch);
   k_tridiag<<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, ldfx, ldx);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+int fdbs_tridiag_rows(void *vctx, double *d_fx, const double *d_x, int64_t batch, int64_t ldfx, int64_t ldx, void *stream) {
+  fdbs_tridiag_rows_ctx *c = (fdbs_tridiag_rows_ctx *)vctx;
+  if (!c || batch < 1 || batch > 65535) return 1;
+  c->calls += batch;
+  if (c->nrows <= 0) return 0;
+  dim3 grid((unsigned)blocks_for(c->nrows), (unsigned)batch);
+  k_tridiag_rows<<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, c->row0, c->nrows, c->x0, ldfx, ldx);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -199,3 +199,168 @@ class ShardedJacobian:
         if self._ipc is not None:
             self._ipc.free()
             self._ipc = None
+
+
+# ------------------------------------------------------------------------------------------------ column-block shards
+# problems with fewer colours than GPUs (C2: 3 colours, C3: 5) cannot be spread by colour.  A
+# contiguous block of COLUMNS can: the block's entries live in a row range [r0, r1), those rows depend on an x range
+# [x0, x1) (the block plus a halo), and everything the colour loop does for the block happens inside those ranges —
+# with a slice-aware f! (rows [r0, r1) from x[x0:x1]) there is no exchange at all on the data path.  The only global
+# quantity is the step size of each colour (norm over ALL colour-k components of x, jacobians.jl:559-561): every rank
+# holds the full x and runs the K2 pass on it (fdb_color_eps), the shard plan takes the result as external step sizes.
+# With the same step sizes a shard's values are bit-identical to its segment of the unsharded nzval.
+def column_blocks(colptr, world: int) -> List[int]:
+    """Block boundaries b[0..world] (0-based columns) balancing the number of stored entries per block."""
+    cp = colptr.cpu().numpy() if isinstance(colptr, torch.Tensor) else np.asarray(colptr)
+    n = len(cp) - 1
+    nnz = int(cp[-1] - 1)
+    bounds = [0]
+    for r in range(1, world):
+        target = 1 + (nnz * r) // world
+        bounds.append(int(min(max(np.searchsorted(cp, target, side="left"), bounds[-1]), n)))
+    bounds.append(n)
+    return bounds
+
+
+class EpsPlan:
+    """Step sizes of every colour for a full-length x: the K2 pass alone (fdb_eps_plan_create / fdb_color_eps)."""
+
+    def __init__(self, n: int, colorvec, fdtype, device):
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        o = api._opts(api._fdtype_code(fdtype), api._device_index(device))
+        cv_ptr, keep = api._index_ptr(colorvec)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().fdb_eps_plan_create(C.byref(h), int(n), cv_ptr, C.byref(o)))
+        self.plan = api.Plan(h.value, keep=(keep,))
+        self.n_colors = self.plan.info()["n_colors"]
+        self.eps = torch.zeros(max(self.n_colors, 1), dtype=torch.float64, device=self.device)
+
+    def compute(self, x: torch.Tensor, relstep=None, absstep=None, dir=True, stream=None) -> torch.Tensor:
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            L.check(L.lib().fdb_color_eps(self.plan.handle, x.data_ptr(), 0.0 if relstep is None else float(relstep),
+                                          0.0 if absstep is None else float(absstep), float(dir), self.eps.data_ptr(),
+                                          C.c_void_p(stream)))
+        return self.eps
+
+
+class ColumnBlockJacobian:
+    """The colour loop of finite_difference_jacobian! for the columns [c0, c1) of a CSC Jacobian.
+
+    f_factory(row0, row1, x0, x1) must return the slice-aware f! (NativeFn or Python callable f(fx, x)) that computes
+    rows [row0, row1) of f from x[x0:x1] (0-based, half-open).  run(x, eps) writes the block's values into
+    values_ptr (default: J.nzval) at slots [p0, p1) — the same positions the unsharded call writes."""
+
+    def __init__(self, J: api.SparseMatrixCSC, colorvec, fdtype, c0: int, c1: int, device, f_factory, *, max_batch=1,
+                 use_graph=False, no_drift=False):
+        self.device = torch.device(device)
+        self.fdtype = fdtype
+        cp = J.colptr if isinstance(J.colptr, torch.Tensor) else torch.as_tensor(np.asarray(J.colptr))
+        rv = J.rowval if isinstance(J.rowval, torch.Tensor) else torch.as_tensor(np.asarray(J.rowval))
+        cp, rv = cp.to(self.device), rv.to(self.device)
+        n = J.n
+        self.c0, self.c1 = int(c0), int(c1)
+        self.p0, self.p1 = int(cp[c0]) - 1, int(cp[c1]) - 1
+        seg = rv[self.p0:self.p1]
+        if seg.numel() == 0:
+            self.r0 = self.r1 = 0
+            self.x0, self.x1 = self.c0, self.c1
+        else:
+            self.r0, self.r1 = int(seg.min()) - 1, int(seg.max())
+            # hull of the columns with an entry in rows [r0, r1) (rows are sorted inside a column)
+            cnt = cp[1:] - cp[:-1]
+            first = rv[(cp[:-1] - 1).clamp(max=max(rv.numel() - 1, 0))]
+            last = rv[(cp[1:] - 2).clamp(min=0)]
+            touch = (cnt > 0) & (last - 1 >= self.r0) & (first - 1 < self.r1)
+            idx = torch.nonzero(touch).reshape(-1)
+            self.x0, self.x1 = min(int(idx[0]), self.c0), max(int(idx[-1]) + 1, self.c1)
+        self.m_loc, self.n_loc = self.r1 - self.r0, self.x1 - self.x0
+        # local pattern: only the owned columns carry entries
+        j = torch.arange(self.x0, self.x1 + 1, device=self.device)
+        colptr_loc = (cp[j.clamp(self.c0, self.c1)] - self.p0).contiguous()
+        rowval_loc = (seg - self.r0).contiguous()
+        if isinstance(colorvec, range):
+            colorvec = np.arange(colorvec.start, colorvec.stop, colorvec.step, dtype=np.int64)
+        cv = colorvec if isinstance(colorvec, torch.Tensor) else torch.as_tensor(np.asarray(colorvec, dtype=np.int64))
+        self.cv_loc = cv[self.x0:self.x1].to(self.device).contiguous()
+        self.sub = api.SparseMatrixCSC(self.m_loc, self.n_loc, colptr_loc, rowval_loc, None)
+        self.values_default = J.nzval
+        self.plan = api.make_plan(self.sub, self.sub, self.cv_loc, fdtype, self.n_loc, self.device, max_batch=max_batch,
+                                  use_graph=use_graph, no_drift=no_drift)
+        self.f = f_factory(self.r0, self.r1, self.x0, self.x1)
+        self._fn = api._as_fn(self.f, self.m_loc, self.n_loc, self.device, 1)
+        self._eps_set = None
+
+    def run(self, x: torch.Tensor, eps: torch.Tensor, values_ptr: Optional[int] = None, dir=True, stream=None):
+        addr, ctx, pyfn = self._fn
+        if self._eps_set != eps.data_ptr():
+            L.check(L.lib().fdb_plan_set_external_eps(self.plan.handle, eps.data_ptr()))
+            self._eps_set = eps.data_ptr()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        base = self.values_default.data_ptr() if values_ptr is None else int(values_ptr)
+        with torch.cuda.device(self.device):
+            st = L.lib().fdb_jacobian(self.plan.handle, addr, ctx, x.data_ptr() + 8 * self.x0, base + 8 * self.p0, None,
+                                      None, 0.0, 0.0, float(dir), C.c_void_p(stream))
+        if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
+            exc, pyfn.exc = pyfn.exc, None
+            raise exc
+        L.check(st)
+
+
+class ColumnShardedJacobian:
+    """One process per GPU, every rank owns a contiguous block of columns (entry-balanced).  Every rank needs the full
+    x; J stays column-sharded (gather=None: rank r's J.nzval holds its slots [p0, p1)) or is assembled on rank 0
+    (gather="root": the scatter kernel stores straight into rank 0's nzval over NVLink — contiguous 16-byte stores)."""
+
+    def __init__(self, J: api.SparseMatrixCSC, colorvec, fdtype, device, f_factory, *, gather: Optional[str] = None,
+                 group=None, max_batch=1, use_graph=False):
+        if gather not in (None, "root"):
+            raise ValueError("gather must be None or 'root'")
+        self.J, self.device, self.group, self.gather = J, torch.device(device), group, gather
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.bounds = column_blocks(J.colptr, self.world)
+        self.eps_plan = EpsPlan(J.n, colorvec, fdtype, device)
+        self.block = ColumnBlockJacobian(J, colorvec, fdtype, self.bounds[self.rank], self.bounds[self.rank + 1], device,
+                                         f_factory, max_batch=max_batch, use_graph=use_graph)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._ipc: Optional[IpcBuffer] = None
+        self._root_ptr = None
+        if gather == "root":
+            handles = [None] * self.world
+            mine = None
+            if self.rank == 0:
+                self._ipc = IpcBuffer(J.nzval.numel(), self.device)
+                self._ipc.tensor.copy_(J.nzval)
+                J.nzval = self._ipc.tensor
+                self.block.values_default = J.nzval
+                mine = self._ipc.handle()
+            dist.all_gather_object(handles, mine, group=group)
+            if self.rank != 0:
+                p = C.c_void_p()
+                with torch.cuda.device(self.device):
+                    L.check(L.lib().fdb_ipc_open(handles[0], C.byref(p)))
+                self._root_ptr = p.value
+
+    def run(self, x: torch.Tensor, dir=True):
+        eps = self.eps_plan.compute(x, dir=dir)
+        if self.gather == "root":
+            dist.all_reduce(self.flag, group=self.group)      # rank 0 is done reading the previous J
+        self.block.run(x, eps, values_ptr=self._root_ptr, dir=dir)
+        if self.gather == "root":
+            dist.all_reduce(self.flag, group=self.group)      # every block (incl. its peer stores) has completed
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if self._root_ptr:
+            with torch.cuda.device(self.device):
+                L.lib().fdb_ipc_close(C.c_void_p(self._root_ptr))
+            self._root_ptr = None
+        try:
+            dist.barrier(group=self.group)
+        except Exception:
+            pass
+        if self._ipc is not None:
+            self._ipc.free()

@@ -207,6 +207,24 @@ fdb_status fdb_jacobian_complex(fdb_plan *plan, fdb_fn_c f, void *ctx, const dou
 fdb_status fdb_jacobian_host(fdb_plan *plan, fdb_fn f, void *ctx, const double *h_x, double *h_J, double *h_fx,
                              const double *h_f_in, double relstep, double absstep, double dir);
 
+/* ---- Column-block sharding (problems with fewer colours than GPUs) -------------------------------
+ * A shard is a plan over a contiguous block of columns of the sparsity (its colptr slice rebased to 1, row indices
+ * rebased to the first row the block touches), evaluated on the slice of x that those rows depend on, with a
+ * slice-aware f! (the callback's ctx carries the row / x offsets).  The reference takes every colour's step size from
+ * the norm over ALL colour-k components of x (jacobians.jl:559-561), so a shard must not derive it from its slice:
+ *   fdb_eps_plan_create   plan that only knows (n, colorvec) of the FULL problem,
+ *   fdb_color_eps         eps[k] of every colour for a full-length device x (the K2 pass alone), left in the plan
+ *                         (fdb_plan_get_eps) and optionally copied to d_eps_out (device, n_colors doubles); also valid
+ *                         on any coloured Jacobian plan,
+ *   fdb_plan_set_external_eps   makes a Jacobian plan copy its step sizes from d_eps (device, at least the plan's
+ *                         n_colors entries, read on the call's stream) instead of running its own K2 pass; NULL
+ *                         restores the built-in pass.  With the same eps the shard's values are bit-identical to the
+ *                         corresponding segment of the unsharded Jacobian. */
+fdb_status fdb_eps_plan_create(fdb_plan **plan, int64_t n, const int64_t *colorvec, const fdb_plan_opts *opts);
+fdb_status fdb_color_eps(fdb_plan *plan, const double *d_x, double relstep, double absstep, double dir,
+                         double *d_eps_out, void *stream);
+fdb_status fdb_plan_set_external_eps(fdb_plan *plan, const double *d_eps);
+
 /* ---- Jacobian-vector product: finite_difference_jvp!(jvp, f, x, v, cache::JVPCache, f_in; relstep, absstep, dir)
  *      src/jvp.jl:238-274 — eps from sqrt(abs(dot(x, v))) (computed on the device), forward: f(fx1,x), f(jvp,x+eps v);
  *      central: f(fx1, x-eps v) then f(jvp, x+eps v).  opts->fdtype selects forward/central (complex is rejected like
