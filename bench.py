@@ -358,12 +358,33 @@ def gpu_arm(args):
     J, f, x, cache = prob["J"], prob["f"], prob["x"], prob["cache"]
 
     sharded = None
-    if world > 1:
+    colsharded = None
+    if world > 1 and args.shard == "columns":
+        # contiguous column blocks + slice-aware f! (few-colour problems): only the tridiagonal workloads have one here
+        if workload not in ("c1", "c2") or fdtype == "complex":
+            raise SystemExit("--shard columns is benchmarked on the tridiagonal workloads (c1, c2), forward / central")
         from finitediff_jl_b200 import distributed as fdist
+        n_glob = prob["n"]
+        keep_ctx = []
+
+        def factory(r0, r1, x0, x1):
+            c = L.TridiagRowsCtx(n_glob, r0, r1 - r0, x0, 0)
+            keep_ctx.append(c)
+            return pkg.NativeFn(C.cast(L.synth().fdbs_tridiag_rows, C.c_void_p).value, c, max_batch=args.max_batch)
+
+        colsharded = fdist.ColumnShardedJacobian(J, prob["keep"][2], fdtype, dev, factory,
+                                                 gather=None if args.gather == "none" else "root",
+                                                 max_batch=args.max_batch, use_graph=args.graph)
+    elif world > 1:
+        from finitediff_jl_b200 import distributed as fdist
+        if args.gather == "none":
+            raise SystemExit("--gather none needs --shard columns")
         sharded = fdist.ShardedJacobian(J, cache, x.numel(), dev, gather=args.gather)
 
     def step():
-        if sharded is not None:
+        if colsharded is not None:
+            colsharded.run(x)
+        elif sharded is not None:
             sharded.run(f, x)
         else:
             pkg.finite_difference_jacobian_(J, f, x, cache)
@@ -385,7 +406,7 @@ def gpu_arm(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    plan = cache._last_plan
+    plan = colsharded.block.plan if colsharded is not None else cache._last_plan
     info = plan.info()
     nnz = prob["nnz"] if prob["nnz"] is not None else info["n_entries"]
     c0 = plan.counters()
@@ -431,7 +452,7 @@ def gpu_arm(args):
     # ---- roofline of the dominant kernel (diff+scatter), this rank
     peak, peak_src = peaks()
     alg_bytes = info["alg_bytes_scatter"]
-    if world > 1 and workload != "c5":
+    if world > 1 and workload != "c5" and colsharded is None:
         alg_bytes = alg_bytes * info["n_local_colors"] // max(info["n_colors"], 1)
     scat_per_jac = scat_ms / tsteps if tsteps else 0.0
     launches_per_jac = scat_n / tsteps if tsteps else 0
@@ -498,7 +519,7 @@ def gpu_arm(args):
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(workload, fdtype), "cuda_graph": bool(args.graph), "l2": "inputs larger than L2 (no flush needed): x, the stacked "
                        "f! outputs and nzval total far more than 126 MB per step" if workload != "c1" else "C1 is L2-resident (latency config)",
-                       "max_batch": args.max_batch, "gather": args.gather if world > 1 else None, "colors_local": info["n_local_colors"], "scatter_groups": info["n_groups"],
+                       "max_batch": args.max_batch, "gather": args.gather if world > 1 else None, "shard": args.shard if world > 1 else None, "colors_local": info["n_local_colors"], "scatter_groups": info["n_groups"],
                        "first_call_ms": first_call_ms},
             "f_evals_per_s": f_points_all / (ms_total * 1e-3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
@@ -522,9 +543,13 @@ def main():
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch eagerly instead of replaying the captured CUDA graph of the call")
-    ap.add_argument("--gather", default="root", choices=["all", "root", "all_p2p"],
+    ap.add_argument("--gather", default="root", choices=["all", "root", "all_p2p", "none"],
                     help="N>1: rank 0 ends with the full Jacobian (root: fused NVLink gather), or every rank does "
                          "(all: root gather + NCCL broadcast; all_p2p: every value stored to every peer)")
+    ap.add_argument("--shard", default="colors", choices=["colors", "columns"],
+                    help="N>1: what is partitioned over the GPUs — the colour set (default; c4) or contiguous column "
+                         "blocks with a slice-aware f! (c2: 3 colours cannot be spread over more than 3 GPUs); with "
+                         "columns, --gather root assembles J on rank 0, --gather none leaves it column-sharded")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-scale", type=float, default=None, dest="cpu_scale",

@@ -136,4 +136,25 @@ function finite_difference_jacobian!(J::DeviceCSC, f, x::CuVector{Float64},
     nothing                                  # jacobians.jl:652
 end
 
+# ---- column-block shards (few-colour problems on several GPUs): one process per GPU, each owning the columns c0+1:c1.
+# `sub` is the block's pattern (colptr slice rebased to 1, rows rebased to the block's first row), `f_rows!` computes
+# that row range from the x slice the rows depend on, `eps` holds the step sizes of the FULL x (color_eps below).
+function color_eps!(eps::CuVector{Float64}, epsplan::Plan, x::CuVector{Float64}; relstep = 0.0, absstep = 0.0, dir = true)
+    check(ccall((:fdb_color_eps, libfdjac), Cint,
+        (Ptr{Cvoid}, CuPtr{Float64}, Float64, Float64, Float64, CuPtr{Float64}, Ptr{Cvoid}),
+        epsplan.handle, pointer(x), relstep, absstep, Float64(dir), pointer(eps), CUDA.stream().handle))
+    eps
+end
+
+function eps_plan(n::Integer, colorvec::Vector{Int64}, fd::Cint)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    opts = Ref(PlanOpts(fd))
+    check(ccall((:fdb_eps_plan_create, libfdjac), Cint, (Ptr{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{PlanOpts}),
+        h, n, colorvec, opts))
+    Plan(h[])
+end
+
+set_external_eps!(plan::Plan, eps::CuVector{Float64}) =
+    check(ccall((:fdb_plan_set_external_eps, libfdjac), Cint, (Ptr{Cvoid}, CuPtr{Float64}), plan.handle, pointer(eps)))
+
 end # module

@@ -116,6 +116,41 @@ def _worker(rank, world, port, out_dir):
                      ctx=orc.SynthRank1Ctx(nd, w.ctypes.data_as(C.POINTER(C.c_double)), 1))
         assert np.array_equal(Jslab.cpu().numpy(), ref[b * nd: e * nd]), f"rank {rank} dense slab"
         assert ctx.calls == 2 * (e - b)
+        # column-block shards (few-colour problem): every rank owns a block of columns; J sharded, then gathered on rank 0
+        from _util import cyc_colors, tridiag_csc
+        nt = 30011
+        cpt, rvt = tridiag_csc(nt)
+        cvt = cyc_colors(nt, 3)
+        xt = torch.from_numpy(orc.fill_x(nt, 9)).to(dev)
+        for fdtype in ("forward", "central"):
+            octx_t = orc.SynthTridiagCtx(nt, 1)
+            for gather in (None, "root"):
+                Jt = pkg.SparseMatrixCSC(nt, nt, torch.from_numpy(cpt).to(dev), torch.from_numpy(rvt).to(dev),
+                                         torch.full((len(rvt),), float("nan"), dtype=torch.float64, device=dev))
+                keep = []
+
+                def factory(r0, r1, x0, x1):
+                    c = L.TridiagRowsCtx(nt, r0, r1 - r0, x0, 0)
+                    keep.append(c)
+                    return pkg.NativeFn(C.cast(L.synth().fdbs_tridiag_rows, C.c_void_p).value, c)
+
+                cs = fdist.ColumnShardedJacobian(Jt, cvt, fdtype, dev, factory, gather=gather)
+                for _ in range(2):
+                    cs.run(xt)
+                torch.cuda.synchronize()
+                dist.barrier()
+                eps = cs.eps_plan.plan.eps()
+                ref = np.full(len(rvt), np.nan)
+                orc.jacobian(orc.Problem.csc_same(nt, nt, cpt, rvt), ref, orc.native_fn("synth_tridiag"), orc.fill_x(nt, 9),
+                             fdtype=0 if fdtype == "forward" else 1, colorvec=cvt, eps_override=eps, ctx=octx_t)
+                got = Jt.nzval.cpu().numpy()
+                if gather == "root" and rank == 0:
+                    assert np.array_equal(got, ref), f"column shards gathered on root, {fdtype}"
+                elif gather is None:
+                    b = cs.block
+                    assert np.array_equal(got[b.p0:b.p1], ref[b.p0:b.p1]), f"rank {rank} column block {fdtype}"
+                    assert np.isnan(got[:b.p0]).all() and np.isnan(got[b.p1:]).all()
+                cs.close()
         (Path(out_dir) / f"ok_{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
