@@ -17,3 +17,23 @@ for _ in range(5):
     a.record(); dst.copy_(src); b.record(); torch.cuda.synchronize()
     best = min(best, a.elapsed_time(b))
 print("copy_", f"{best:.3f} ms  {2*src.numel()*8/best/1e6:.1f} GB/s (read+write)")
+
+# non-constant data: broadcast a 40 MB (L2-resident) random row into the 16 GB tensor — the same traffic shape as the
+# banded whole-band fill (16 GB written, sources served from L2)
+del src, dst
+row = torch.rand(5_000_000, dtype=torch.float64, device="cuda")
+tv = t.view(400, 5_000_000)
+best = 1e9
+for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); tv.copy_(row.view(1, -1).expand(400, -1)); b.record(); torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+print("broadcast-copy of a 40 MB row", f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s written")
+
+# non-constant data with NO reads: arange writes index values (is the 7.5 TB/s of fill_ specific to constant data?)
+best = 1e9
+for _ in range(5):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); torch.arange(n, dtype=torch.float64, out=t); b.record(); torch.cuda.synchronize()
+    best = min(best, a.elapsed_time(b))
+print("arange (non-constant, store-only)", f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s written")

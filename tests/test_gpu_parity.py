@@ -421,11 +421,12 @@ def lap5_csc(g):
     return A
 
 
+@pytest.mark.parametrize("g", [120, 121])
 @pytest.mark.parametrize("fdtype", ["forward", "central"])
-def test_lap5_csc_and_banded_bitexact(pkg, oracle, dev, fdtype):
+def test_lap5_csc_and_banded_bitexact(pkg, oracle, dev, fdtype, g):
     """2-D 5-point stencil (coloring_tests.jl:99-108 shape; BASELINE config C3 at reduced g): CSC path and the
     whole-band BandedMatrix path (ext/FiniteDiffBandedMatricesExt.jl:13-27, incl. its spurious in-band entries)."""
-    g = 120
+    # even and odd band half-widths (the flat-stream band kernel cuts the band storage into 16-byte aligned chunks)
     n = g * g
     A = lap5_csc(g)
     colptr, rowval = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1
@@ -491,6 +492,40 @@ def test_narrow_band_and_rectangular_band(pkg, oracle, dev):
         pkg.finite_difference_jacobian_(Jb, f_t, x, cache)
         ref = np.full((l + u + 1) * n, np.nan)
         oracle.jacobian(oracle.Problem.banded(m, n, l, u), ref, f_n, xh.copy(), colorvec=cv,
+                        eps_override=cache._last_plan.eps())
+        assert np.array_equal(Jb.data.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("m,n,l,u", [(3000, 3000, 64, 64), (2500, 3100, 70, 58), (3100, 2500, 40, 88), (900, 900, 33, 31)])
+def test_wide_band_few_colors_with_colourless_columns(pkg, oracle, dev, m, n, l, u):
+    # few colours on a wide band: quotients pre-divided in place + whole-band copy; columns without a valid colour stay 0
+    # (fill_matrix!), corner slots outside the matrix 0; square / wide / tall, even and odd l+u+1
+    rng = np.random.default_rng(5)
+    cv = cyc_colors(n, 5)
+    cv[rng.integers(0, n, 25)] = 0
+    x = dev_x(pkg, dev, n, 78)
+    xh = oracle.fill_x(n, 78)
+
+    def f_t(fx, xx):
+        k = min(m, n)
+        fx.zero_()
+        fx[:k] = xx[:k] * xx[:k]
+        fx[1:k] += 0.5 * xx[: k - 1]
+
+    def f_n(fx, xx):
+        k = min(m, n)
+        fx[:] = 0
+        fx[:k] = xx[:k] * xx[:k]
+        fx[1:k] += 0.5 * xx[: k - 1]
+
+    for fdtype in ("forward", "central"):
+        Jb = pkg.BandedMatrix(m, n, l, u, device=dev)
+        Jb.data.fill_(float("nan"))
+        cache = pkg.JacobianCache(x, torch.zeros(m, dtype=torch.float64, device=dev),
+                                  torch.zeros(m, dtype=torch.float64, device=dev), fdtype, colorvec=cv, sparsity=Jb)
+        pkg.finite_difference_jacobian_(Jb, f_t, x, cache)
+        ref = np.full((l + u + 1) * n, np.nan)
+        oracle.jacobian(oracle.Problem.banded(m, n, l, u), ref, f_n, xh.copy(), fdtype=FD[fdtype], colorvec=cv,
                         eps_override=cache._last_plan.eps())
         assert np.array_equal(Jb.data.cpu().numpy(), ref)
 
