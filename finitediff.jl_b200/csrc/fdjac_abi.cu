@@ -1077,7 +1077,12 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
           const int32_t CH = (int32_t)std::min<int64_t>(2048, w & ~(int64_t)1);
           const int64_t nchunks = (w * P->n + CH - 1) / CH;
           if (prediv) {
-            const int grid = resident_grid(P, diff_scatter_band_flat<CT, kCopy>, sm, (nchunks + 7) / 8);
+            // unlike the read-modify kernels (C2: no gain), this store-dominated stream gains from an oversubscribed grid:
+            // C3 3.03 ms with exactly one resident wave, 2.72 (x4), 2.48 (x16), 2.38 (x64), 2.40 (one chunk per warp);
+            // a bare store-only probe shows the same trend (6.0 -> 6.7 TB/s, profiles/write_bw_probe.py)
+            constexpr int kBandGridOver = 64;
+            int grid = resident_grid(P, diff_scatter_band_flat<CT, kCopy>, sm, (nchunks + 7) / 8);
+            grid = (int)std::min<int64_t>((int64_t)grid * kBandGridOver, (nchunks + 7) / 8);
             diff_scatter_band_flat<CT, kCopy><<<grid, kThreads, sm, s>>>(a, CH);
           } else {
             const int grid = resident_grid(P, diff_scatter_band_flat<CT, MODE>, sm, (nchunks + 7) / 8);

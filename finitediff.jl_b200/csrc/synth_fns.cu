@@ -171,6 +171,17 @@ inline int blocks_for(int64_t items, int64_t cap = 148 * 8) {
 }
 }  // namespace
 
+// Store-only bandwidth probe: n doubles written once with 16-byte streaming stores, grid-stride in address order.
+// mode 0: one constant; mode 1: a different value per element (rules out constant-data effects in the memory system)
+__global__ void __launch_bounds__(kT) k_store_probe(double *__restrict__ out, int64_t n, int mode) {
+  const int64_t stride = (int64_t)gridDim.x * kT * 2;
+  for (int64_t i = (blockIdx.x * (int64_t)kT + threadIdx.x) * 2; i + 1 < n; i += stride) {
+    const double v0 = mode ? (double)i * 1.0000001 + 0.5 : 1.0;
+    const double v1 = mode ? (double)(i + 1) * 1.0000001 + 0.5 : 1.0;
+    __stcs(reinterpret_cast<double2 *>(out + i), make_double2(v0, v1));
+  }
+}
+
 extern "C" {
 
 int fdbs_tridiag(void *vctx, double *d_fx, const double *d_x, int64_t batch, int64_t ldfx, int64_t ldx, void *stream) {
@@ -243,6 +254,12 @@ int fdbs_fail(void *, double *, const double *, int64_t, int64_t, int64_t, void 
 int fdbs_fill_x(double *d_x, int64_t n, uint64_t seed, void *stream) {
   if (n <= 0) return 0;
   k_fill_x<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(d_x, n, seed);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
+}
+
+int fdbs_store_probe(double *d_out, int64_t n, int mode, int blocks, void *stream) {
+  if (n <= 0 || blocks <= 0) return 1;
+  k_store_probe<<<blocks, kT, 0, (cudaStream_t)stream>>>(d_out, n, mode);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -37,6 +37,8 @@ int fdbs_fail(void *ctx, double *d_fx, const double *d_x, int64_t batch, int64_t
 /* x[i] = 0.5 + u_i, u_i from splitmix64(seed, i): same generator as oracle/synth_fns.c:synth_fill_x */
 int fdbs_fill_x(double *d_x, int64_t n, uint64_t seed, void *stream);
 /* write a buffer larger than L2 (flushes L2 between timed iterations) */
+/* store-only bandwidth probe (profiles/write_bw_probe.py): mode 0 constant data, mode 1 a distinct value per element */
+int fdbs_store_probe(double *d_out, int64_t n, int mode, int blocks, void *stream);
 int fdbs_flush_l2(void *d_buf, int64_t bytes, void *stream);
 
 #ifdef __cplusplus

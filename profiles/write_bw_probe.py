@@ -30,10 +30,17 @@ for _ in range(5):
     best = min(best, a.elapsed_time(b))
 print("broadcast-copy of a 40 MB row", f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s written")
 
-# non-constant data with NO reads: arange writes index values (is the 7.5 TB/s of fill_ specific to constant data?)
-best = 1e9
-for _ in range(5):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); torch.arange(n, dtype=torch.float64, out=t); b.record(); torch.cuda.synchronize()
-    best = min(best, a.elapsed_time(b))
-print("arange (non-constant, store-only)", f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s written")
+# store-only stream from our own probe kernel (16-byte streaming stores, grid-stride): constant vs distinct values,
+# persistent grid (8 blocks/SM) — is the 7.5 TB/s of fill_ specific to constant data?
+import sys, pathlib
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+import _bootstrap
+synth = _bootstrap.load_package()._lib.synth()
+for mode, name in ((0, "constant"), (1, "distinct values")):
+    for blocks in (148 * 8, 148 * 32):
+        best = 1e9
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); synth.fdbs_store_probe(t.data_ptr(), n, mode, blocks, None); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        print(f"store probe, {name}, {blocks} blocks", f"{best:.3f} ms  {n*8/best/1e6:.1f} GB/s written")
