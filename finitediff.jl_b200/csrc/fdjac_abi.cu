@@ -1211,12 +1211,17 @@ static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, d
       TRY(call_f(P, f, ctx, P->Fm, P->xp, kc, s));                       // f(fx, x1)    :596
       P->cnt.kernel_launches += 1;
     }
-    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((P->m + kThreads * 4 - 1) / (kThreads * 4), (int64_t)P->sm_count * 8 / kc + 1));
+    // a store-heavy stream (24 bytes moved per 8 written): many small blocks rather than one resident wave — each thread
+    // handles about four row pairs (see the band kernel's grid note)
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((P->m / 2 + kThreads * 4 - 1) / (kThreads * 4), 64));
     dim3 grid((unsigned)gx, (unsigned)kc);
     {
+      const double *lo_ptr = CENTRAL ? P->Fm : vfx;
+      const int pairs_ok = ((reinterpret_cast<uintptr_t>(J + c0l * P->ldJ) | reinterpret_cast<uintptr_t>(lo_ptr) |
+                             reinterpret_cast<uintptr_t>(P->Fp)) & 15) == 0 && (P->ldJ & 1) == 0 && (sF & 1) == 0;
       ScatterTimer tm(P, s);
-      diff_columns<MODE><<<grid, kThreads, 0, s>>>(P->Fp, CENTRAL ? P->Fm : vfx, P->eps_cols, c0l, kc, P->m, sF, P->ldJ,
-                                                   J + c0l * P->ldJ);
+      diff_columns<MODE><<<grid, kThreads, 0, s>>>(P->Fp, lo_ptr, P->eps_cols, c0l, kc, P->m, sF, P->ldJ,
+                                                   J + c0l * P->ldJ, pairs_ok);
     }
     P->cnt.kernel_launches += 2;
     P->cnt.scatter_launches += 1;

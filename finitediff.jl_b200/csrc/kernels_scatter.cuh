@@ -544,7 +544,8 @@ diff_scatter_band(const BandArgs a) {
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx, const double *__restrict__ eps_local,
-             int64_t col0_local, int32_t B, int64_t m, int64_t ldF, int64_t ldJ, double *__restrict__ Jcols) {
+             int64_t col0_local, int32_t B, int64_t m, int64_t ldF, int64_t ldJ, double *__restrict__ Jcols,
+             int pairs_ok /* every column of hi / lo / out is 16-byte aligned */) {
   // grid.y = column within the batch, grid.x strides over rows
   const int b = blockIdx.y;
   if (b >= B) return;
@@ -553,6 +554,19 @@ diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx,
   const double *lo = MODE == kCentral ? Fm_or_fx + (int64_t)b * ldF : Fm_or_fx;
   double *out = Jcols + (int64_t)b * ldJ;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
+  if (pairs_ok && MODE != kComplex) {
+    // two rows per lane: 16-byte streaming loads of the slabs (read once) and 16-byte streaming stores of the column;
+    // f(x) (forward) is re-read by every column and stays cacheable
+    const double denom = MODE == kCentral ? 2 * e : e;
+    const int64_t m2 = m >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < m2; i += stride) {
+      const double2 h = ld_stream2(hi + 2 * i);
+      const double2 l = MODE == kCentral ? ld_stream2(lo + 2 * i) : __ldg(reinterpret_cast<const double2 *>(lo + 2 * i));
+      st_stream2(out + 2 * i, (h.x - l.x) / denom, (h.y - l.y) / denom);
+    }
+    if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[m - 1] = fd_quotient<MODE>(hi, lo, m - 1, e);
+    return;
+  }
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < m; i += stride)
     st_stream(out + i, fd_quotient<MODE>(hi, lo, i, e));
 }

@@ -665,9 +665,10 @@ def test_different_pattern_csc_J(pkg, oracle, dev):
 
 @pytest.mark.parametrize("fdtype", ["forward", "central"])
 @pytest.mark.parametrize("batch", [1, 7])
-def test_dense_columns_bitexact(pkg, oracle, dev, fdtype, batch):
-    """sparsity === nothing: dense column branch (jacobians.jl:548-557, :590-598), BASELINE config C5 shape at reduced n."""
-    n = 300
+@pytest.mark.parametrize("n", [300, 301])
+def test_dense_columns_bitexact(pkg, oracle, dev, fdtype, batch, n):
+    """sparsity === nothing: dense column branch (jacobians.jl:548-557, :590-598), BASELINE config C5 shape at reduced n
+    (even n: 16-byte row pairs; odd n: columns are only 8-byte aligned -> scalar rows)."""
     w = np.random.default_rng(2).random(n)
     d_w = torch.from_numpy(w).to(dev)
     nblk = (n + 1023) // 1024
