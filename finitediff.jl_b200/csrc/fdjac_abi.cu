@@ -978,10 +978,16 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
         if (COMPLEX) {
           if (pa.kcount == 1) perturb_complex<CT, 1><<<P->grid(P->n), kThreads, 0, s>>>(pa);
           else perturb_complex<CT, kPerturbMaxPoints><<<P->grid(P->n), kThreads, 0, s>>>(pa);
-        } else if (pa.kcount == 1)
-          perturb_colors<CT, CENTRAL, 1><<<resident_grid(P, perturb_colors<CT, CENTRAL, 1>, sm, tiles), kThreads, sm, s>>>(pa);
-        else
-          perturb_colors<CT, CENTRAL, kPerturbMaxPoints><<<resident_grid(P, perturb_colors<CT, CENTRAL, kPerturbMaxPoints>, sm, tiles), kThreads, sm, s>>>(pa);
+        } else {
+          // store-heavy (NP points written per element read): an oversubscribed grid, like the band and dense-column
+          // kernels (C2 step, 1x -> 16x the resident wave: forward 0.299 -> 0.291 ms, central 0.424 -> 0.408 ms)
+          constexpr int kPerturbGridOver = 16;
+          auto over = [&](int g) { return (int)std::min<int64_t>((int64_t)g * kPerturbGridOver, tiles); };
+          if (pa.kcount == 1)
+            perturb_colors<CT, CENTRAL, 1><<<over(resident_grid(P, perturb_colors<CT, CENTRAL, 1>, sm, tiles)), kThreads, sm, s>>>(pa);
+          else
+            perturb_colors<CT, CENTRAL, kPerturbMaxPoints><<<over(resident_grid(P, perturb_colors<CT, CENTRAL, kPerturbMaxPoints>, sm, tiles)), kThreads, sm, s>>>(pa);
+        }
         P->cnt.kernel_launches += 1;
       }
       return FDB_OK;
