@@ -97,6 +97,14 @@ def main():
         "x": x.tolist(),
         "bounds": {"forward": 1e-6, "central": 1e-8},
     }
+    # --- finitedifftests.jl:600-605: identity map at ones(2), cache-less in-place call, all three fdtypes, J ≈ I ---
+    out["identity2"] = {
+        "cite": "test/finitedifftests.jl:600-605",
+        "x": [1.0, 1.0],
+        "J_expected": [[1.0, 0.0], [0.0, 1.0]],
+        "fdtypes": ["forward", "central", "complex"],
+        "rtol": float(np.sqrt(np.finfo(float).eps)),       # Julia's isapprox default for Float64
+    }
     # --- epsilons.jl:134-144 defaults ---
     out["default_relstep"] = {
         "cite": "src/epsilons.jl:134-144",

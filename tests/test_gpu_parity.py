@@ -788,3 +788,20 @@ def test_window_eps_lane_groups(pkg, oracle, dev, kind):
     oracle.jacobian(oracle.Problem.csc_same(n, n, colptr, rowval), ref, oracle.native_fn("synth_tridiag"), xh.copy(),
                     colorvec=cv, eps_override=eps, ctx=oracle.SynthTridiagCtx(n, 1))
     assert np.array_equal(J.nzval.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("fdtype", ["forward", "central", "complex"])
+def test_kat_identity_map_all_fdtypes(pkg, golden, dev, fdtype):
+    # finitedifftests.jl:600-605: in-place Jacobian of the identity map at ones(2), every fdtype: J ≈ I; the caller's x is
+    # untouched (the cache-less entry builds exactly this cache: api.finite_difference_jacobian_, jacobians.jl:456-467)
+    g = golden["identity2"]
+    x = torch.tensor(g["x"], dtype=torch.float64, device=dev)
+
+    def ident(out, xx):
+        out.copy_(xx)
+
+    J = pkg.zeros_colmajor(2, 2, dev)
+    J.fill_(float("nan"))
+    pkg.finite_difference_jacobian_(J, ident, x, pkg.JacobianCache(x, fdtype))
+    np.testing.assert_allclose(J.cpu().numpy(), np.array(g["J_expected"]), rtol=g["rtol"], atol=g["rtol"])
+    assert torch.equal(x.cpu(), torch.tensor(g["x"], dtype=torch.float64))

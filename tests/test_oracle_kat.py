@@ -329,3 +329,23 @@ def test_threads_match_single_thread(oracle):
     b = np.zeros(len(rowval))
     oracle.jacobian(P, b, f_tridiag, x.copy(), colorvec=cv, nthreads=4, eps_override=r["eps"])
     assert (a == b).all()
+
+
+def test_identity_map_all_fdtypes(oracle, golden):
+    # finitedifftests.jl:600-605: J of (out, in) -> out .= in at ones(2), cache-less in-place call, every fdtype: J ≈ I
+    g = golden["identity2"]
+    x = np.array(g["x"])
+    Jexp = np.array(g["J_expected"])
+
+    def ident(out, xx):
+        out[:] = xx
+
+    for fd in g["fdtypes"]:
+        J = np.full(4, np.nan)
+        if fd == "complex":
+            r = oracle.jacobian_complex(oracle.Problem.dense(2, 2), J, ident, x.copy())
+            assert r["fcalls"] == 2
+        else:
+            r = oracle.jacobian(oracle.Problem.dense(2, 2), J, ident, x.copy(), fdtype=0 if fd == "forward" else 1)
+            assert r["fcalls"] == (3 if fd == "forward" else 4)
+        np.testing.assert_allclose(J.reshape(2, 2, order="F"), Jexp, rtol=g["rtol"], atol=g["rtol"])
