@@ -982,7 +982,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
           // store-heavy (NP points written per element read): an oversubscribed grid, like the band and dense-column
           // kernels (C2 step, 1x -> 16x the resident wave: forward 0.299 -> 0.291 ms, central 0.424 -> 0.408 ms)
           constexpr int kPerturbGridOver = 16;
-          auto over = [&](int g) { return (int)std::min<int64_t>((int64_t)g * kPerturbGridOver, tiles); };
+          auto over = [&](int g) { return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)g * kPerturbGridOver, tiles)); };
           if (pa.kcount == 1)
             perturb_colors<CT, CENTRAL, 1><<<over(resident_grid(P, perturb_colors<CT, CENTRAL, 1>, sm, tiles)), kThreads, sm, s>>>(pa);
           else
@@ -1088,7 +1088,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             // a bare store-only probe shows the same trend (6.0 -> 6.7 TB/s, profiles/write_bw_probe.py)
             constexpr int kBandGridOver = 64;
             int grid = resident_grid(P, diff_scatter_band_flat<CT, kCopy>, sm, (nchunks + 7) / 8);
-            grid = (int)std::min<int64_t>((int64_t)grid * kBandGridOver, (nchunks + 7) / 8);
+            grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)grid * kBandGridOver, (nchunks + 7) / 8));
             diff_scatter_band_flat<CT, kCopy><<<grid, kThreads, sm, s>>>(a, CH);
           } else {
             const int grid = resident_grid(P, diff_scatter_band_flat<CT, MODE>, sm, (nchunks + 7) / 8);
