@@ -222,6 +222,33 @@ def column_blocks(colptr, world: int) -> List[int]:
     return bounds
 
 
+def block_geometry(colptr: torch.Tensor, rowval: torch.Tensor, c0: int, c1: int) -> dict:
+    """Everything a column block [c0, c1) of a CSC pattern (Int64, 1-based, rows sorted inside a column) needs:
+    p0, p1   0-based slot range of the block in rowval / nzval,
+    r0, r1   the row range its entries touch (0-based, half-open),
+    x0, x1   hull of the columns with an entry in those rows = the x slice a slice-aware f! must see (contains [c0, c1)),
+    colptr_loc / rowval_loc   the block's pattern over the columns [x0, x1) and rows [r0, r1), 1-based: only the owned
+             columns carry entries."""
+    cp, rv = colptr, rowval
+    p0, p1 = int(cp[c0]) - 1, int(cp[c1]) - 1
+    seg = rv[p0:p1]
+    if seg.numel() == 0:
+        r0 = r1 = 0
+        x0, x1 = c0, c1
+    else:
+        r0, r1 = int(seg.min()) - 1, int(seg.max())
+        cnt = cp[1:] - cp[:-1]
+        first = rv[(cp[:-1] - 1).clamp(max=max(rv.numel() - 1, 0))]
+        last = rv[(cp[1:] - 2).clamp(min=0)]
+        touch = (cnt > 0) & (last - 1 >= r0) & (first - 1 < r1)
+        idx = torch.nonzero(touch).reshape(-1)
+        x0, x1 = min(int(idx[0]), c0), max(int(idx[-1]) + 1, c1)
+    j = torch.arange(x0, x1 + 1, device=cp.device)
+    colptr_loc = (cp[j.clamp(c0, c1)] - p0).contiguous()
+    rowval_loc = (seg - r0).contiguous()
+    return dict(p0=p0, p1=p1, r0=r0, r1=r1, x0=x0, x1=x1, colptr_loc=colptr_loc, rowval_loc=rowval_loc)
+
+
 class EpsPlan:
     """Step sizes of every colour for a full-length x: the K2 pass alone (fdb_eps_plan_create / fdb_color_eps)."""
 
@@ -260,27 +287,11 @@ class ColumnBlockJacobian:
         cp = J.colptr if isinstance(J.colptr, torch.Tensor) else torch.as_tensor(np.asarray(J.colptr))
         rv = J.rowval if isinstance(J.rowval, torch.Tensor) else torch.as_tensor(np.asarray(J.rowval))
         cp, rv = cp.to(self.device), rv.to(self.device)
-        n = J.n
         self.c0, self.c1 = int(c0), int(c1)
-        self.p0, self.p1 = int(cp[c0]) - 1, int(cp[c1]) - 1
-        seg = rv[self.p0:self.p1]
-        if seg.numel() == 0:
-            self.r0 = self.r1 = 0
-            self.x0, self.x1 = self.c0, self.c1
-        else:
-            self.r0, self.r1 = int(seg.min()) - 1, int(seg.max())
-            # hull of the columns with an entry in rows [r0, r1) (rows are sorted inside a column)
-            cnt = cp[1:] - cp[:-1]
-            first = rv[(cp[:-1] - 1).clamp(max=max(rv.numel() - 1, 0))]
-            last = rv[(cp[1:] - 2).clamp(min=0)]
-            touch = (cnt > 0) & (last - 1 >= self.r0) & (first - 1 < self.r1)
-            idx = torch.nonzero(touch).reshape(-1)
-            self.x0, self.x1 = min(int(idx[0]), self.c0), max(int(idx[-1]) + 1, self.c1)
+        g = block_geometry(cp, rv, self.c0, self.c1)
+        self.p0, self.p1, self.r0, self.r1, self.x0, self.x1 = g["p0"], g["p1"], g["r0"], g["r1"], g["x0"], g["x1"]
         self.m_loc, self.n_loc = self.r1 - self.r0, self.x1 - self.x0
-        # local pattern: only the owned columns carry entries
-        j = torch.arange(self.x0, self.x1 + 1, device=self.device)
-        colptr_loc = (cp[j.clamp(self.c0, self.c1)] - self.p0).contiguous()
-        rowval_loc = (seg - self.r0).contiguous()
+        colptr_loc, rowval_loc = g["colptr_loc"], g["rowval_loc"]
         if isinstance(colorvec, range):
             colorvec = np.arange(colorvec.start, colorvec.stop, colorvec.step, dtype=np.int64)
         cv = colorvec if isinstance(colorvec, torch.Tensor) else torch.as_tensor(np.asarray(colorvec, dtype=np.int64))

@@ -28,6 +28,54 @@ def test_column_blocks_balance_entries_cpu():
     assert b2[0] == 0 and b2[-1] == 2 and all(b2[i] <= b2[i + 1] for i in range(4))
 
 
+@pytest.mark.parametrize("seed,world", [(0, 1), (1, 2), (2, 3), (3, 5), (4, 8)])
+def test_block_geometry_cpu(seed, world):
+    # pure host logic of the column-block shards on CPU tensors: the blocks tile nzval, every block's rows / x hull
+    # contain everything its slice-aware f! needs, the local pattern is the block's pattern rebased
+    import scipy.sparse as sps
+    import _bootstrap
+    _bootstrap.load_package()
+    from finitediff_jl_b200 import distributed as fdist
+    rng = np.random.default_rng(seed)
+    m, n = 61, 53
+    bw_lo, bw_hi = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+    D = np.zeros((m, n), bool)
+    for c in range(n):
+        for r in range(max(0, c - bw_hi), min(m, c + bw_lo + 1)):
+            D[r, c] = rng.random() < 0.7
+    D[:, rng.integers(0, n)] = False                                   # an empty column
+    A = sps.csc_matrix(D)
+    A.sort_indices()
+    colptr = torch.from_numpy(A.indptr.astype(np.int64) + 1)
+    rowval = torch.from_numpy(A.indices.astype(np.int64) + 1)
+    bounds = fdist.column_blocks(colptr, world)
+    covered = np.zeros(A.nnz, int)
+    for r in range(world):
+        c0, c1 = bounds[r], bounds[r + 1]
+        g = fdist.block_geometry(colptr, rowval, c0, c1)
+        covered[g["p0"]:g["p1"]] += 1
+        assert g["x0"] <= c0 and c1 <= g["x1"]
+        sub = D[:, c0:c1]
+        if sub.any():
+            rows = np.nonzero(sub.any(axis=1))[0]
+            assert g["r0"] == rows.min() and g["r1"] == rows.max() + 1
+            need = np.nonzero(D[g["r0"]:g["r1"], :].any(axis=0))[0]    # columns the rows [r0, r1) depend on
+            assert g["x0"] <= need.min() and need.max() < g["x1"]
+        else:
+            assert g["p0"] == g["p1"] and g["r0"] == g["r1"]
+        # local pattern == the block's columns of D, rows rebased, placed at columns [c0 - x0, c1 - x0) of the slice
+        cpl, rvl = g["colptr_loc"].numpy(), g["rowval_loc"].numpy()
+        assert len(cpl) == g["x1"] - g["x0"] + 1 and cpl[0] == 1 and cpl[-1] == g["p1"] - g["p0"] + 1
+        loc = np.zeros((max(g["r1"] - g["r0"], 0), g["x1"] - g["x0"]), bool)
+        for jl in range(g["x1"] - g["x0"]):
+            for q in range(cpl[jl] - 1, cpl[jl + 1] - 1):
+                loc[rvl[q] - 1, jl] = True
+        expect = np.zeros_like(loc)
+        expect[:, c0 - g["x0"]:c1 - g["x0"]] = D[g["r0"]:g["r1"], c0:c1]
+        assert np.array_equal(loc, expect)
+    assert (covered == 1).all()
+
+
 @pytest.fixture(scope="module")
 def pkg():
     if not torch.cuda.is_available():
