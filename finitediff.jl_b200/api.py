@@ -78,6 +78,19 @@ def _index_ptr(a):
     return arr.ctypes.data, arr
 
 
+def _is_identity_colorvec(colorvec, n: int) -> bool:
+    """colorvec == 1:n (the JacobianCache default, jacobians.jl:16), whatever container holds it."""
+    if colorvec is None:
+        return True
+    if isinstance(colorvec, range):
+        return colorvec == range(1, n + 1)
+    if isinstance(colorvec, torch.Tensor):
+        return colorvec.numel() == n and bool(torch.equal(colorvec.reshape(-1).cpu().to(torch.int64),
+                                                          torch.arange(1, n + 1, dtype=torch.int64)))
+    arr = np.asarray(colorvec).reshape(-1)
+    return arr.size == n and bool(np.array_equal(arr, np.arange(1, n + 1)))
+
+
 def _index_key(a):
     if a is None:
         return None
@@ -451,8 +464,16 @@ def make_plan(J, sparsity, colorvec, fdtype, x_len: int, device, **plan_kw) -> P
     cv_ptr, cv_keep = _index_ptr(colorvec)
     keep = [cv_keep]
     if sparsity is None:
-        # dense column branch: J dense, colorvec ignored except that it must be the default (jacobians.jl:548-557)
+        # dense column branch (jacobians.jl:548-557): column i of J from perturbing component i, colorvec = 1:n.
+        # With sparsity === nothing and any OTHER colorvec the reference loops color_i in 1:maximum(colorvec) and
+        # perturbs COMPONENT color_i (the colour id used as an index), touching only those leading columns of J — a
+        # quirk of the reference this path does not reproduce: refuse rather than return a different J.
         m, n, ld = _dense_ld(J)
+        if colorvec is not None and not _is_identity_colorvec(colorvec, n):
+            raise NotImplementedError(
+                "sparsity=None with a non-default colorvec: the reference computes only J[:, 1:maximum(colorvec)] by "
+                "perturbing components 1:maximum(colorvec) (jacobians.jl:547-557); pass the sparsity pattern the "
+                "colouring belongs to, or leave colorvec at its default 1:length(x)")
         L.check(lib.fdb_plan_create_dense(C.byref(h), m, n, ld, C.byref(o)))
     elif isinstance(sparsity, SparseMatrixCSC):
         cp, k1 = _index_ptr(sparsity.colptr)

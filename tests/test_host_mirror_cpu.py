@@ -73,3 +73,20 @@ def test_cpu_inputs_rejected_loudly(pkg):
         pkg.JacobianCache(x, "forward")
     with pytest.raises(TypeError):
         pkg.finite_difference_jacobian_(pkg.zeros_colmajor(4, 4, "cpu"), lambda a, b: None, x, "forward")
+
+
+def test_identity_colorvec_detection(pkg):
+    # the dense column branch (sparsity === nothing) is only the reference's behaviour for colorvec == 1:n
+    # (jacobians.jl:547-557); the mirror refuses any other colorvec there, whatever container holds it
+    import numpy as np
+    import torch
+    api = pkg.api
+    assert api._is_identity_colorvec(None, 5)
+    assert api._is_identity_colorvec(range(1, 6), 5)
+    assert not api._is_identity_colorvec(range(1, 5), 5)
+    assert api._is_identity_colorvec(np.arange(1, 6), 5)
+    assert api._is_identity_colorvec([1, 2, 3, 4, 5], 5)
+    assert not api._is_identity_colorvec(np.array([1, 2, 1, 2, 1]), 5)
+    assert api._is_identity_colorvec(torch.arange(1, 6), 5)
+    assert not api._is_identity_colorvec(torch.tensor([1, 2, 3, 4, 4]), 5)
+    assert not api._is_identity_colorvec(torch.arange(1, 5), 5)
