@@ -404,7 +404,11 @@ static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, in
   P->use_graph = o && o->use_graph != 0;
   P->world = (o && o->world > 1) ? o->world : 1;
   P->rank = (o && o->world > 1) ? o->rank : 0;
-  if (P->rank < 0 || P->rank >= P->world) { delete P; return fail(FDB_ERR_INVALID, "rank %d outside world %d", P->rank, P->world); }
+  if (P->rank < 0 || P->rank >= P->world) {
+    const int bad_rank = P->rank, bad_world = P->world;
+    delete P;
+    return fail(FDB_ERR_INVALID, "rank %d outside world %d", bad_rank, bad_world);
+  }
   cudaDeviceProp prop;
   cudaError_t e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) { delete P; return fail(FDB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
