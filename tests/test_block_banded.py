@@ -117,3 +117,75 @@ def test_block_banded_dense_blocks_structure(pkg, oracle):
     Jd = np.zeros(n * n)
     oracle.jacobian(oracle.Problem.dense(n, n), Jd, f_lap5(g), x.copy())
     np.testing.assert_allclose(Jb, Jd.reshape(n, n, order="F"), rtol=1e-6, atol=1e-6)   # Jbb ≈ Jsparse (coloring_tests.jl:119)
+
+
+def _literal_bbb_writes(rb, l, u, lam, mu, colorvec):
+    """ext/FiniteDiffBlockBandedMatricesExt.jl:16-42 transcribed: for each colour, the (row, col, in-block slot) triples
+    the hook stores to, in its own loop order (block column J, block row K in blockcolrange, column j, row k)."""
+    N = len(rb)
+    off = np.concatenate([[0], np.cumsum(rb)])
+    out = {}
+    for color_i in range(1, int(max(colorvec)) + 1):
+        w = []
+        for J in range(1, N + 1):
+            c_v = colorvec[off[J - 1]:off[J]]                       # c.blocks[J]
+            for K in range(max(1, J - u), min(N, J + l) + 1):       # blockcolrange(Jac, J)
+                m, n = rb[K - 1], rb[J - 1]                         # size(view(Jac, K, J))
+                for j in range(1, n + 1):
+                    if c_v[j - 1] == color_i:
+                        for k in range(max(1, j - mu), min(m, j + lam) + 1):
+                            w.append((off[K - 1] + k, off[J - 1] + j, mu + k - j + 1))   # unsafe_store! offset in the column
+        out[color_i] = w
+    return out
+
+
+def _literal_blockbanded_writes(rb, l, u, colorvec):
+    """ext/FiniteDiffBlockBandedMatricesExt.jl:44-68 transcribed (dense blocks inside the block band)."""
+    N = len(rb)
+    off = np.concatenate([[0], np.cumsum(rb)])
+    out = {}
+    for color_i in range(1, int(max(colorvec)) + 1):
+        w = []
+        for J in range(1, N + 1):
+            c_v = colorvec[off[J - 1]:off[J]]
+            for j in range(1, rb[J - 1] + 1):
+                if c_v[j - 1] == color_i:
+                    for K in range(max(1, J - u), min(N, J + l) + 1):
+                        for k in range(1, rb[K - 1] + 1):
+                            w.append((off[K - 1] + k, off[J - 1] + j))
+        out[color_i] = w
+    return out
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_block_banded_entry_sets_match_literal_hooks_cpu(pkg, seed):
+    # host logic only (no GPU): the entry sets the mirror hands to the slot-addressed scatter are exactly what the
+    # reference's two block-banded hooks store to, colour by colour
+    rng = np.random.default_rng(seed)
+    N = int(rng.integers(1, 6))
+    rb = [int(b) for b in rng.integers(1, 7, N)]
+    l, u = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+    lam, mu = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+    n = sum(rb)
+    cv = rng.integers(1, 5, n).astype(np.int64)
+    B = pkg.BandedBlockBandedMatrix(rb, rb, (l, u), (lam, mu), device="cpu")
+    rows, cols, slots = B.findstructralnz()
+    lit_w = _literal_bbb_writes(rb, l, u, lam, mu, cv)
+    for color_i, w in lit_w.items():
+        sel = cv[cols - 1] == color_i
+        got = sorted(zip(rows[sel].tolist(), cols[sel].tolist()))
+        assert got == sorted((r, c) for r, c, _ in w)
+    assert len(set(slots.tolist())) == len(slots) and slots.min(initial=1) >= 1 and slots.max(initial=1) <= B.w * n
+    # sub-band position inside the block's band column is the reference's unsafe_store! offset (mu + k - j + 1)
+    sw = lam + mu + 1
+    key = {(r, c): s for r, c, s in (t for w in lit_w.values() for t in w)}
+    for r, c, s in zip(rows.tolist(), cols.tolist(), slots.tolist()):
+        assert ((s - 1) % B.w) % sw + 1 == key[(r, c)]
+    # dense blocks
+    BB = pkg.BlockBandedMatrix(rb, rb, (l, u), device="cpu")
+    r2, c2, s2 = BB.findstructralnz()
+    lit2 = _literal_blockbanded_writes(rb, l, u, cv)
+    for color_i, w in lit2.items():
+        sel = cv[c2 - 1] == color_i
+        assert sorted(zip(r2[sel].tolist(), c2[sel].tolist())) == sorted(w)
+    assert len(set(s2.tolist())) == len(s2)
