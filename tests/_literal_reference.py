@@ -242,3 +242,30 @@ def finite_difference_jvp(jvp, f, x, v, cache, f_in=None, *, fdtype="forward", r
     else:
         raise ValueError("fdtype")
     return {"eps": epsilon, "fcalls": calls}
+
+
+_DEFAULT = object()
+
+
+def finite_difference_jacobian_cacheless(J, f, x, fdtype="forward", f_in=None, *, relstep=None, absstep=None,
+                                         colorvec=None, sparsity=_DEFAULT):
+    """The cache-less method (jacobians.jl:446-471): builds the cache, evaluates f(fx, x) itself in forward mode and
+    forwards cache.fx as f_in.  Returns dict(eps, fcalls)."""
+    m, n = _size(J)
+    if colorvec is None:
+        colorvec = np.arange(1, len(x) + 1)                    # :454
+    if sparsity is _DEFAULT:
+        sparsity = J if isinstance(J, (CSC, Banded)) else None # :455  ArrayInterface.has_sparsestruct(J) ? J : nothing
+    extra = 0
+    if f_in is None and fdtype == "forward":
+        fx = np.zeros_like(x) if m == len(x) else np.zeros(m)  # :457-461
+        f(fx, x); extra = 1                                    # :462
+        cache = dict(x1=x.copy(), x2=np.zeros_like(x), fx=fx, fx1=fx.copy())          # JacobianCache(x, fx, ...) :50-57
+    elif f_in is None:
+        cache = dict(x1=x.copy(), x2=np.zeros_like(x), fx=np.zeros(m), fx1=np.zeros(m))
+    else:
+        cache = dict(x1=x.copy(), x2=np.zeros_like(x), fx=f_in, fx1=f_in.copy())
+    r = finite_difference_jacobian(J, f, x, cache, cache["fx"], fdtype=fdtype, relstep=relstep, absstep=absstep,
+                                   colorvec=colorvec, sparsity=sparsity)               # :469-470
+    r["fcalls"] += extra
+    return r

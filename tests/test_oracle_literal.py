@@ -185,3 +185,38 @@ def test_oracle_jvp_matches_literal_transcription(oracle, seed):
     ro2 = oracle.jvp(f, x.copy(), v.copy(), m, fdtype=FD[fdtype], f_in=f_in, eps_override=rl["eps"], **kw)
     assert np.array_equal(ro2["jvp"], out)
     assert np.array_equal(ro2["x1"][:n], cache["x1"])          # cache.x1 ends as x + eps*v
+
+
+@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("kind", ["csc_same", "banded", "dense_cols"])
+def test_oracle_cacheless_matches_literal_transcription(oracle, kind, seed):
+    # jacobians.jl:446-471: the method without a cache (sparsity defaults to J when J has structure)
+    rng = np.random.default_rng(91000 + 1000 * seed + KINDS.index(kind))
+    m, n, l, u, D, f = _problem(rng, kind)
+    fdtype = "forward" if rng.random() < 0.5 else "central"
+    x = rng.uniform(-2, 2, n)
+    if kind == "dense_cols":
+        cv = None
+    else:
+        cv = rng.integers(1, int(rng.integers(1, 7)) + 1, n).astype(np.int64)
+    A = sps.csc_matrix(D)
+    A.sort_indices()
+    colptr, rowval = A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1
+    if kind == "csc_same":
+        J = lit.CSC(m, n, colptr, rowval, np.full(A.nnz, np.nan))
+        P = oracle.Problem.csc_same(m, n, colptr, rowval)
+    elif kind == "banded":
+        J = lit.Banded(m, n, l, u, np.full((l + u + 1, n), np.nan))
+        P = oracle.Problem.banded(m, n, l, u)
+    else:
+        J = np.full((m, n), np.nan)
+        P = oracle.Problem.dense(m, n)
+    xl = x.copy()
+    rl = lit.finite_difference_jacobian_cacheless(J, f, xl, fdtype, colorvec=cv)
+    Jl = J.nzval if isinstance(J, lit.CSC) else (J.data if isinstance(J, lit.Banded) else J).reshape(-1, order="F")
+    Jo = np.full(Jl.size, np.nan)
+    ro = oracle.jacobian(P, Jo, f, x.copy(), fdtype=FD[fdtype], colorvec=cv, cacheless=True,
+                         eps_override=None if kind == "dense_cols" else rl["eps"])
+    assert ro["fcalls"] == rl["fcalls"] == ((1 if fdtype == "forward" else 0) +
+                                            (n if cv is None else int(cv.max())) * (1 if fdtype == "forward" else 2))
+    assert np.array_equal(Jo, Jl, equal_nan=True), f"{kind} {fdtype} seed {seed}"
