@@ -3,7 +3,7 @@
 Layout (only what the path needs):
     csrc/      hand-written CUDA kernels + the C ABI (libfdjac_b200.so; include/fdjac_b200.h)
     api.py     host-side mirror of the reference interface (JacobianCache / finite_difference_jacobian!)
-    distributed.py  one-process-per-GPU colour partition + fused gather plumbing
+    distributed.py  multi-GPU plumbing over the C ABI's fdb_group_* / fdb_sync_* (colour shards, column blocks)
     julia/     the `ccall` wrapper a Julia host would load (not executable in this image: no julia)
     _lib.py    ctypes binding of the C ABI (fails loudly if the .so is missing)
     build.py   nvcc recipe (sm_100a only)
@@ -12,10 +12,10 @@ The directory name contains a dot, so it is imported through /root/repo/_bootstr
 `finitediff_jl_b200`.
 """
 from . import _lib  # noqa: F401
-from .api import (BandedBlockBandedMatrix, BandedMatrix, BlockBandedMatrix, JacobianCache, JVPCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
+from .api import (BandedBlockBandedMatrix, BandedMatrix, BlockBandedMatrix, DenseColumnBlock, JacobianCache, JVPCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
                   default_relstep, finite_difference_jacobian_, finite_difference_jacobian_b, finite_difference_jvp_,
                   make_plan, pinned_empty, resize_, zeros_colmajor)
 
-__all__ = ["BandedBlockBandedMatrix", "BandedMatrix", "BlockBandedMatrix", "JacobianCache", "JVPCache", "finite_difference_jvp_", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
+__all__ = ["BandedBlockBandedMatrix", "BandedMatrix", "BlockBandedMatrix", "DenseColumnBlock", "JacobianCache", "JVPCache", "finite_difference_jvp_", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
            "default_relstep", "finite_difference_jacobian_", "finite_difference_jacobian_b", "make_plan",
            "pinned_empty", "resize_", "zeros_colmajor"]

@@ -16,6 +16,8 @@ SYNTH_PATH = HERE / "libfdjac_synth.so"
 FDB_OK, FDB_ERR_INVALID, FDB_ERR_CUDA, FDB_ERR_CALLBACK, FDB_ERR_NOMEM, FDB_ERR_UNSUPPORTED, FDB_ERR_NO_DEVICE = range(7)
 FDB_FORWARD, FDB_CENTRAL, FDB_COMPLEX = 0, 1, 2
 FDB_J_CSC_NZVAL, FDB_J_DENSE, FDB_J_BAND, FDB_J_SLOTS = 0, 1, 2, 3
+# FDB_STEP_DEFAULT: relstep / absstep keyword not given (any other value, 0 included, is used as passed)
+STEP_DEFAULT = float("nan")
 
 # int (*fdb_fn)(void* ctx, double* d_fx, const double* d_x, int64 batch, int64 ldfx, int64 ldx, void* stream)
 FDB_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
@@ -26,7 +28,7 @@ class PlanOpts(C.Structure):
         ("fdtype", C.c_int32), ("device", C.c_int32), ("use_current_device", C.c_int32), ("no_drift", C.c_int32),
         ("max_batch", C.c_int64), ("scratch_bytes", C.c_int64),
         ("rank", C.c_int32), ("world", C.c_int32), ("partition", C.c_int32), ("strategy", C.c_int32),
-        ("use_graph", C.c_int32), ("reserved", C.c_int32),
+        ("use_graph", C.c_int32), ("shared_j", C.c_int32),
     ]
 
 
@@ -37,6 +39,7 @@ class PlanInfo(C.Structure):
         ("fcalls_per_jacobian", C.c_int64), ("device_bytes", C.c_int64),
         ("fdtype", C.c_int32), ("jkind", C.c_int32), ("sp_kind", C.c_int32), ("color_bits", C.c_int32),
         ("alg_bytes_scatter", C.c_int64), ("strategy", C.c_int32), ("lanes", C.c_int32), ("mean_row_jump", C.c_double),
+        ("moved_bytes_scatter", C.c_int64),
     ]
 
     def as_dict(self):
@@ -64,6 +67,7 @@ ABI_SYMBOLS = {
     "fdb_plan_create_coo": (_int, [_PP, _i64, _i64, _i64, _vp, _vp, _int, _vp, _i64, _vp, C.POINTER(PlanOpts)]),
     "fdb_plan_create_banded": (_int, [_PP, _i64, _i64, _i64, _i64, _int, _i64, _vp, C.POINTER(PlanOpts)]),
     "fdb_plan_create_dense": (_int, [_PP, _i64, _i64, _i64, C.POINTER(PlanOpts)]),
+    "fdb_plan_create_dense_colorvec": (_int, [_PP, _i64, _i64, _i64, _vp, C.POINTER(PlanOpts)]),
     "fdb_plan_destroy": (_int, [_vp]),
     "fdb_plan_info": (_int, [_vp, C.POINTER(PlanInfo)]),
     "fdb_plan_counters": (_int, [_vp, C.POINTER(Counters)]),
@@ -79,6 +83,18 @@ ABI_SYMBOLS = {
     "fdb_eps_plan_create": (_int, [_PP, _i64, _vp, C.POINTER(PlanOpts)]),
     "fdb_color_eps": (_int, [_vp, _vp, _f64, _f64, _f64, _vp, _vp]),
     "fdb_plan_set_external_eps": (_int, [_vp, _vp]),
+    "fdb_group_create_csc": (_int, [_PP, _int, C.POINTER(_int), _i64, _i64, _vp, _vp, _int, _vp, _vp, _i64, _vp, C.POINTER(PlanOpts)]),
+    "fdb_group_create_banded": (_int, [_PP, _int, C.POINTER(_int), _i64, _i64, _i64, _i64, _int, _i64, _vp, C.POINTER(PlanOpts)]),
+    "fdb_group_create_dense": (_int, [_PP, _int, C.POINTER(_int), _i64, _i64, _i64, C.POINTER(PlanOpts)]),
+    "fdb_group_destroy": (_int, [_vp]),
+    "fdb_group_size": (_int, [_vp, C.POINTER(_int)]),
+    "fdb_group_plan": (_int, [_vp, _int, _PP]),
+    "fdb_group_jacobian": (_int, [_vp, _vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
+    "fdb_sync_create": (_int, [_PP, _int, _int, _int]),
+    "fdb_sync_flags": (_int, [_vp, _PP]),
+    "fdb_sync_set_peers": (_int, [_vp, C.POINTER(_vp)]),
+    "fdb_sync_barrier": (_int, [_vp, _vp]),
+    "fdb_sync_destroy": (_int, [_vp]),
     "fdb_jvp_plan_create": (_int, [_PP, _i64, _i64, C.POINTER(PlanOpts)]),
     "fdb_jvp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_host_alloc": (_int, [_PP, C.c_size_t]),

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
+import zlib
 from typing import Callable, Optional
 
 import numpy as np
@@ -28,7 +29,7 @@ import torch
 from . import _lib as L
 
 __all__ = [
-    "SparseMatrixCSC", "BandedMatrix", "Tridiagonal", "BandedBlockBandedMatrix", "NativeFn", "JacobianCache", "Plan",
+    "SparseMatrixCSC", "BandedMatrix", "Tridiagonal", "BandedBlockBandedMatrix", "DenseColumnBlock", "NativeFn", "JacobianCache", "Plan",
     "finite_difference_jacobian_", "finite_difference_jacobian_b", "resize_", "default_relstep", "compute_epsilon",
     "zeros_colmajor", "pinned_empty",
 ]
@@ -101,7 +102,14 @@ def _index_key(a):
     arr = np.asarray(a)
     if arr.size <= 4096:
         return ("v", arr.shape, arr.astype(np.int64).tobytes())
-    return ("n", arr.__array_interface__["data"][0], arr.size)
+    # large host arrays: identity + a strided content sample (4096 elements, first and last included), so that an
+    # in-place edit of colorvec / colptr / rowval is noticed in all but contrived cases without an O(n) pass on every
+    # call.  The plan holds a private compressed copy: after an in-place edit that the sample cannot see, call
+    # cache.invalidate() (documented in JacobianCache).
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 4096)
+    sample = np.ascontiguousarray(flat[::step]).tobytes() + np.ascontiguousarray(flat[-1:]).tobytes()
+    return ("n", arr.__array_interface__["data"][0], arr.size, zlib.crc32(sample))
 
 
 def zeros_colmajor(m: int, n: int, device="cuda") -> torch.Tensor:
@@ -305,6 +313,21 @@ class BlockBandedMatrix(BandedBlockBandedMatrix):
         super().__init__(rowblocks, colblocks, blockbandwidths, (full, full), data=data, device=device)
 
 
+class DenseColumnBlock:
+    """Columns [col0, col0+ncols) of a dense m x n Jacobian held by ONE rank (north_star config 5: the dense Jacobian is
+    column-partitioned over the GPUs and may stay that way): `slab` is the rank's own column-major (m, ncols) storage.
+    Use it as J with a JacobianCache built with rank=, world= and sparsity=None; the plan's column range must be the
+    block (checked on first use)."""
+
+    def __init__(self, m, n, col0, ncols, device="cuda", slab=None):
+        self.m, self.n, self.col0, self.ncols = int(m), int(n), int(col0), int(ncols)
+        self.slab = zeros_colmajor(self.m, max(self.ncols, 1), device) if slab is None else slab
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+
 def _findstructralnz_dense(A):
     """src/jacobians.jl:473-488: column-major scan of a dense 0/1 prototype."""
     A = np.asarray(A.cpu() if isinstance(A, torch.Tensor) else A)
@@ -372,10 +395,11 @@ class _PyFn:
 class Plan:
     """Owner of an fdb_plan* (the per-(pattern, colorvec, fdtype) state)."""
 
-    def __init__(self, handle: int, keep=()):
+    def __init__(self, handle: int, keep=(), owned: bool = True):
         self._h = C.c_void_p(handle)
         self._keep = keep
-        self._fin = weakref.finalize(self, L.lib().fdb_plan_destroy, C.c_void_p(handle))
+        # members of an fdb_group are owned (and destroyed) by the group: owned=False gives a plain view
+        self._fin = weakref.finalize(self, L.lib().fdb_plan_destroy, C.c_void_p(handle)) if owned else (lambda: None)
 
     @property
     def handle(self):
@@ -428,10 +452,10 @@ class Plan:
 
 
 def _opts(fdtype, device_index, *, no_drift=False, max_batch=1, scratch_bytes=0, rank=0, world=1, partition=0,
-          strategy=0, use_graph=False):
+          strategy=0, use_graph=False, shared_j=False):
     return L.PlanOpts(fdtype=fdtype, device=device_index, use_current_device=0, no_drift=int(bool(no_drift)),
                       max_batch=int(max_batch), scratch_bytes=int(scratch_bytes), rank=int(rank), world=int(world),
-                      partition=int(partition), strategy=int(strategy), use_graph=int(bool(use_graph)), reserved=0)
+                      partition=int(partition), strategy=int(strategy), use_graph=int(bool(use_graph)), shared_j=int(bool(shared_j)))
 
 
 def _device_index(device) -> int:
@@ -441,6 +465,8 @@ def _device_index(device) -> int:
 
 def _dense_ld(J: torch.Tensor):
     """(m, n, ldJ) of a column-major dense J (Julia Matrix).  Row-major tensors are rejected loudly."""
+    if isinstance(J, DenseColumnBlock):
+        return J.m, J.n, max(int(J.slab.stride(1)) if J.slab.dim() == 2 and J.slab.shape[1] > 1 else J.m, J.m, 1)
     if J.dim() == 1:
         return J.shape[0], 1, max(J.shape[0], 1)
     m, n = J.shape
@@ -466,15 +492,13 @@ def make_plan(J, sparsity, colorvec, fdtype, x_len: int, device, **plan_kw) -> P
     if sparsity is None:
         # dense column branch (jacobians.jl:548-557): column i of J from perturbing component i, colorvec = 1:n.
         # With sparsity === nothing and any OTHER colorvec the reference loops color_i in 1:maximum(colorvec) and
-        # perturbs COMPONENT color_i (the colour id used as an index), touching only those leading columns of J — a
-        # quirk of the reference this path does not reproduce: refuse rather than return a different J.
+        # perturbs COMPONENT color_i (the colour id used as an index), writing only those leading columns of J (J is
+        # not zero-filled on this branch) — reproduced as written by fdb_plan_create_dense_colorvec.
         m, n, ld = _dense_ld(J)
         if colorvec is not None and not _is_identity_colorvec(colorvec, n):
-            raise NotImplementedError(
-                "sparsity=None with a non-default colorvec: the reference computes only J[:, 1:maximum(colorvec)] by "
-                "perturbing components 1:maximum(colorvec) (jacobians.jl:547-557); pass the sparsity pattern the "
-                "colouring belongs to, or leave colorvec at its default 1:length(x)")
-        L.check(lib.fdb_plan_create_dense(C.byref(h), m, n, ld, C.byref(o)))
+            L.check(lib.fdb_plan_create_dense_colorvec(C.byref(h), m, n, ld, cv_ptr, C.byref(o)))
+        else:
+            L.check(lib.fdb_plan_create_dense(C.byref(h), m, n, ld, C.byref(o)))
     elif isinstance(sparsity, SparseMatrixCSC):
         cp, k1 = _index_ptr(sparsity.colptr)
         rv, k2 = _index_ptr(sparsity.rowval)
@@ -563,6 +587,8 @@ def _j_values(J):
         return J.buf
     if isinstance(J, BandedBlockBandedMatrix):
         return J.data
+    if isinstance(J, DenseColumnBlock):
+        return J.slab
     return J
 
 
@@ -577,6 +603,8 @@ def _j_key(J):
         return ("bbb", tuple(J.rb), tuple(J.cb), J.l, J.u, J.lam, J.mu)
     if isinstance(J, torch.Tensor):
         return ("dense", tuple(J.shape), tuple(J.stride()))
+    if isinstance(J, DenseColumnBlock):
+        return ("denseblock", J.m, J.n, J.col0, J.ncols, tuple(J.slab.stride()))
     if isinstance(J, np.ndarray):
         return ("hdense", J.shape, J.strides)
     return ("obj", id(J))
@@ -606,6 +634,9 @@ class JacobianCache:
     jacobians.jl:540-542).  x1/x2/fx1 are not touched (documented drop: in the reference they end as x (with drift),
     the last colour's mask*x, and the last colour's divided difference).
     Extra keywords (B200-specific): max_batch, scratch_bytes, no_drift, rank, world, partition.
+    Plans are cached per (typeof(J), sparsity, colorvec, fdtype) and hold private compressed copies of the index arrays:
+    index arrays are treated as immutable while cached (torch tensors are tracked by their version counter, large numpy
+    arrays by identity + a content sample); after editing one in place call `cache.invalidate()`.
     """
 
     def __init__(self, x1, fx=None, fx1=None, fdtype="forward", returntype=torch.float64, *, colorvec=None,
@@ -737,6 +768,8 @@ def finite_difference_jacobian_(J, f, x, cache=None, f_in=None, returntype=None,
     if ncols != n:
         raise ValueError(f"size(J,2)={ncols} != length(x)={n}")
     plan = cache.plan_for(J, sparsity, colorvec, n)
+    if isinstance(J, DenseColumnBlock) and plan.dense_range() != (J.col0, J.col0 + J.ncols):
+        raise ValueError(f"DenseColumnBlock [{J.col0}, {J.col0 + J.ncols}) is not this rank's column block {plan.dense_range()}")
     jv = _j_values(J)
     if not _is_cuda(jv) or jv.dtype != torch.float64:
         raise TypeError("J's value storage must be a float64 CUDA tensor")
@@ -763,8 +796,8 @@ def finite_difference_jacobian_(J, f, x, cache=None, f_in=None, returntype=None,
         fin_ptr = f_in.data_ptr()
     with torch.cuda.device(x.device):
         st = L.lib().fdb_jacobian(plan.handle, addr, ctx, xv.data_ptr(), jv.data_ptr(), cache.fx.data_ptr(), fin_ptr,
-                                  0.0 if relstep is None else float(relstep),
-                                  0.0 if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
+                                  L.STEP_DEFAULT if relstep is None else float(relstep),
+                                  L.STEP_DEFAULT if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
     if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
         exc, pyfn.exc = pyfn.exc, None
         raise exc                                          # user f threw: propagate like Julia does
@@ -846,8 +879,8 @@ def finite_difference_jvp_(jvp, f, x, v, cache=None, f_in=None, *, relstep=None,
         fin_ptr = f_in.reshape(-1).data_ptr()
     with torch.cuda.device(x.device):
         st = L.lib().fdb_jvp(plan.handle, addr, ctx, jv.data_ptr(), xv.data_ptr(), vv.data_ptr(), cache.x1.data_ptr(),
-                             cache.fx1.data_ptr(), fin_ptr, 0.0 if relstep is None else float(relstep),
-                             0.0 if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
+                             cache.fx1.data_ptr(), fin_ptr, L.STEP_DEFAULT if relstep is None else float(relstep),
+                             L.STEP_DEFAULT if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
     if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
         exc, pyfn.exc = pyfn.exc, None
         raise exc
@@ -857,7 +890,7 @@ def finite_difference_jvp_(jvp, f, x, v, cache=None, f_in=None, *, relstep=None,
 
 
 def _shape_of(J):
-    if isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal, BandedBlockBandedMatrix)):
+    if isinstance(J, (SparseMatrixCSC, BandedMatrix, Tridiagonal, BandedBlockBandedMatrix, DenseColumnBlock)):
         return J.shape
     if isinstance(J, torch.Tensor):
         if J.dim() == 1:

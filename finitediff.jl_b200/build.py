@@ -23,8 +23,8 @@ NVCC_FLAGS = [
 ]
 
 TARGETS = {
-    "libfdjac_b200.so": (["fdjac_abi.cu"], ["common.cuh", "kernels_eps.cuh", "kernels_perturb.cuh", "kernels_plan.cuh",
-                                            "kernels_scatter.cuh", "../../include/fdjac_b200.h"]),
+    # every csrc/*.cuh is a dependency (globbed in build(): a header added later cannot be forgotten)
+    "libfdjac_b200.so": (["fdjac_abi.cu"], ["*.cuh", "../../include/fdjac_b200.h"]),
     "libfdjac_synth.so": (["synth_fns.cu"], ["../../include/fdjac_synth.h"]),
 }
 
@@ -55,7 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> dict:
     for name, (srcs, deps) in TARGETS.items():
         out = lib_path(name)
         src_paths = [CSRC / s for s in srcs]
-        dep_paths = src_paths + [(CSRC / d).resolve() for d in deps] + [Path(__file__)]
+        dep_paths = src_paths + [Path(__file__)]
+        for d in deps:
+            dep_paths += sorted(CSRC.glob(d)) if "*" in d else [(CSRC / d).resolve()]
         if force or _stale(out, dep_paths):
             cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(out), *map(str, src_paths)]
             if verbose:

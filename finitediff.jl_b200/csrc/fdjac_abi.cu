@@ -17,6 +17,8 @@
 #include <type_traits>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 #include "kernels_eps.cuh"
 #include "kernels_perturb.cuh"
@@ -110,6 +112,7 @@ struct fdb_plan {
   const double *ext_eps = nullptr;   // step sizes supplied by the caller (fdb_plan_set_external_eps), device, >= C entries
   unsigned int *ticket = nullptr;   // last-block-done counter of color_sumsq_reg
   bool peers_aligned = true;
+  bool shared_J = false;            // member of an fdb_group: J is shared with the other members (root zero-fills it)
   // scratch
   double *fx_own = nullptr, *Fp = nullptr, *Fm = nullptr, *xp = nullptr, *xm = nullptr;
   int64_t slabs = 0, ldF = 0, ldx = 0, batch = 1, n_groups = 0;
@@ -122,6 +125,12 @@ struct fdb_plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_scat[2] = {nullptr, nullptr};
   int32_t *colptr32 = nullptr, *cols_by_color = nullptr;
+  // colour-major entry lists of this rank's colours (strategy 1; built by build_cm_lists)
+  int32_t *cm_row = nullptr;
+  void *cm_slot = nullptr;            // int32 (nzval slot) or int64 (explicit destination: dest != nullptr)
+  int64_t *cm_start = nullptr;        // device [n_local + 1]
+  std::vector<int64_t> cm_start_h;    // host copy; [n_local] .. cm_invalid_end = entries of columns without a valid colour
+  int64_t cm_invalid_end = 0;
   std::vector<int64_t> bucket_start;   // [C+2] offsets into cols_by_color; bucket C = columns without a valid colour
   int lanes = 1;
   double mean_row_jump = 0.0;
@@ -345,7 +354,7 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   if (P->strategy == 1) {
     // per-colour lists: keep only as many f! outputs in flight as stay L2-resident until their scatter (~48 MB)
     const int64_t l2_slabs = std::max<int64_t>(1, (int64_t)48000000 / per_slab);
-    slabs = std::min<int64_t>(slabs, l2_slabs);
+    slabs = std::min<int64_t>(std::min<int64_t>(slabs, l2_slabs), kCmMaxGroup);
   }
   P->slabs = slabs;
   P->n_groups = n_local == 0 ? 0 : (n_local + slabs - 1) / slabs;
@@ -357,7 +366,9 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   int64_t pbatch = std::max<int64_t>(batch, std::min<int64_t>(kPerturbMaxPoints, std::max<int64_t>(n_local, 1)));
   while (pbatch > batch && pbatch * 8 * cw * P->ldx * (central ? 2 : 1) > budget / 8) --pbatch;
   P->pbatch = pbatch;
-  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && P->world > 1;
+  // two output buffers + a side stream: a group's scatter (and its NVLink stores, when peers are set) overlaps the next
+  // group's f! evaluations
+  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs;
   const size_t nbuf = P->double_buffer ? 2 : 1;
   if (P->double_buffer) {
     CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
@@ -373,6 +384,89 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
     TRY(P->alloc_t(&P->Fm, nbuf * (size_t)slabs * P->ldF));
     TRY(P->alloc_t(&P->xm, (size_t)pbatch * P->ldx));
   }
+  return FDB_OK;
+}
+
+// gather kernel for build_cm_lists: block b copies the column bucket of local colour (or of the invalid bucket) b
+__global__ void __launch_bounds__(kThreads)
+cm_gather_cols(const int32_t *__restrict__ cols_by_color, const int64_t *__restrict__ src_start /* [nseg] */,
+               const int64_t *__restrict__ dst_start /* [nseg+1] */, int64_t nseg, int32_t *__restrict__ list_cols) {
+  for (int64_t sgm = blockIdx.x; sgm < nseg; sgm += gridDim.x) {
+    const int64_t s0 = src_start[sgm], d0 = dst_start[sgm], cnt = dst_start[sgm + 1] - d0;
+    for (int64_t i = threadIdx.x; i < cnt; i += kThreads) list_cols[d0 + i] = cols_by_color[s0 + i];
+  }
+}
+
+// Colour-major entry lists of the colours this rank evaluates (CSC plans, strategy 1): see kernels_scatter.cuh.
+static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long long> &count /* entries per colour */) {
+  const int64_t n_local = (int64_t)P->local_colors.size();
+  const int32_t C = P->C;
+  const bool zero_bucket = P->rank == 0 && P->bucket_start[(size_t)C + 1] > P->bucket_start[(size_t)C];
+  const int64_t nseg = n_local + (zero_bucket ? 1 : 0);
+  std::vector<int64_t> src(std::max<int64_t>(nseg, 1), 0), dst((size_t)nseg + 1, 0);
+  P->cm_start_h.assign((size_t)n_local + 1, 0);
+  unsigned long long valid_total = 0;
+  for (int32_t k = 0; k < C; ++k) valid_total += count[(size_t)k];
+  for (int64_t li = 0; li < n_local; ++li) {
+    const int32_t k = P->local_colors[(size_t)li];
+    src[(size_t)li] = P->bucket_start[(size_t)k];
+    dst[(size_t)li + 1] = dst[(size_t)li] + (P->bucket_start[(size_t)k + 1] - P->bucket_start[(size_t)k]);
+    P->cm_start_h[(size_t)li + 1] = P->cm_start_h[(size_t)li] + (int64_t)count[(size_t)k];
+  }
+  int64_t e_local = P->cm_start_h[(size_t)n_local];
+  P->cm_invalid_end = e_local;
+  if (zero_bucket) {
+    src[(size_t)n_local] = P->bucket_start[(size_t)C];
+    dst[(size_t)n_local + 1] = dst[(size_t)n_local] + (P->bucket_start[(size_t)C + 1] - P->bucket_start[(size_t)C]);
+    e_local += P->E - (int64_t)valid_total;
+    P->cm_invalid_end = e_local;
+  }
+  const int64_t ncols = dst[(size_t)nseg];
+  TRY(P->alloc_t(&P->cm_start, (size_t)n_local + 1));
+  CU(cudaMemcpy(P->cm_start, P->cm_start_h.data(), ((size_t)n_local + 1) * 8, cudaMemcpyHostToDevice));
+  TRY(P->alloc_t(&P->cm_row, (size_t)std::max<int64_t>(e_local, 1)));
+  const bool wide = P->dest != nullptr;
+  TRY(P->alloc(&P->cm_slot, (size_t)std::max<int64_t>(e_local, 1) * (wide ? 8 : 4)));
+  if (ncols == 0 || e_local == 0) return FDB_OK;
+  // temporaries (freed below): column list, counts, offsets, scan scratch
+  int64_t *d_src = nullptr, *d_dst = nullptr;
+  int32_t *list_cols = nullptr, *list_cnt = nullptr, *list_off = nullptr;
+  void *d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_src); cudaFree(d_dst); cudaFree(list_cols); cudaFree(list_cnt); cudaFree(list_off); cudaFree(d_tmp);
+  };
+#define CM_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
+    return fail(FDB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  CM_CU(cudaMalloc((void **)&d_src, (size_t)nseg * 8));
+  CM_CU(cudaMalloc((void **)&d_dst, ((size_t)nseg + 1) * 8));
+  CM_CU(cudaMalloc((void **)&list_cols, (size_t)ncols * 4));
+  CM_CU(cudaMalloc((void **)&list_cnt, (size_t)ncols * 4));
+  CM_CU(cudaMalloc((void **)&list_off, (size_t)ncols * 4));
+  CM_CU(cudaMemcpy(d_src, src.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice));
+  CM_CU(cudaMemcpy(d_dst, dst.data(), ((size_t)nseg + 1) * 8, cudaMemcpyHostToDevice));
+  cm_gather_cols<<<(int)std::min<int64_t>(nseg, (int64_t)P->sm_count * 16), kThreads>>>(P->cols_by_color, d_src, d_dst, nseg, list_cols);
+  cm_column_counts<<<P->grid(ncols), kThreads>>>(list_cols, ncols, P->colptr32, list_cnt);
+  CM_CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, list_cnt, list_off, (int)ncols));
+  CM_CU(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+  CM_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, list_cnt, list_off, (int)ncols));
+  {
+    const int lanes = P->lanes;
+    const int64_t blocks = (ncols + (kThreads / lanes) - 1) / (kThreads / lanes);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)P->sm_count * 16));
+    if (wide) cm_expand<int64_t><<<grid, kThreads>>>(list_cols, list_off, ncols, P->colptr32, P->row32, P->dest, lanes, P->cm_row, (int64_t *)P->cm_slot);
+    else cm_expand<int32_t><<<grid, kThreads>>>(list_cols, list_off, ncols, P->colptr32, P->row32, nullptr, lanes, P->cm_row, (int32_t *)P->cm_slot);
+  }
+  // consistency: the last column's end must be the entry total the per-colour counts promised
+  int32_t last_off = 0, last_cnt = 0;
+  CM_CU(cudaMemcpy(&last_off, list_off + (ncols - 1), 4, cudaMemcpyDeviceToHost));
+  CM_CU(cudaMemcpy(&last_cnt, list_cnt + (ncols - 1), 4, cudaMemcpyDeviceToHost));
+  CM_CU(cudaDeviceSynchronize());
+#undef CM_CU
+  cleanup();
+  if ((int64_t)last_off + last_cnt != e_local)
+    return fail(FDB_ERR_INVALID, "internal: colour-major list holds %lld entries, expected %lld", (long long)last_off + last_cnt,
+                (long long)e_local);
   return FDB_OK;
 }
 
@@ -402,6 +496,7 @@ static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, in
   P->fdtype = o ? o->fdtype : FDB_FORWARD;
   P->no_drift = o ? o->no_drift : 0;
   P->use_graph = o && o->use_graph != 0;
+  P->shared_J = o && o->shared_j != 0;
   P->world = (o && o->world > 1) ? o->world : 1;
   P->rank = (o && o->world > 1) ? o->rank : 0;
   if (P->rank < 0 || P->rank >= P->world) {
@@ -436,6 +531,14 @@ static void free_plan(fdb_plan *P) {
     fdb_status s__ = (expr);                             \
     if (s__ != FDB_OK) { free_plan(P); *plan = nullptr; return s__; } \
   } while (0)
+
+// relstep / absstep keywords of jacobians.jl:508-510: `relstep = default_relstep(fdtype, eltype(x)), absstep = relstep`.
+// FDB_STEP_DEFAULT (NaN) means "keyword not given"; every other value — 0 and negatives included — is used as passed
+// (relstep = 0 is a pure absolute step, absstep = 0 a pure relative one, exactly as in the reference).
+static inline void resolve_steps(int fdtype, double &relstep, double &absstep) {
+  if (std::isnan(relstep)) relstep = fdb_default_relstep(fdtype);
+  if (std::isnan(absstep)) absstep = relstep;
+}
 
 // ------------------------------------------------------------------------------------------------ exported: misc
 extern "C" {
@@ -609,6 +712,7 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     P->strategy_auto = want == 0;
   }
   PLAN_TRY(finish_colored_plan(P, opts, cnt));
+  if (P->strategy == 1) PLAN_TRY(build_cm_lists(P, cnt));
   // B_alg = 32*nnz + 16*n + 8 (valid colouring; Int64 indices as at the ABI)
   P->alg_bytes = 32 * nnz + 16 * n + 8;
   {
@@ -711,7 +815,8 @@ fdb_status fdb_plan_create_banded(fdb_plan **plan, int64_t m, int64_t n, int64_t
   return FDB_OK;
 }
 
-fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const fdb_plan_opts *opts) {
+// dense column branch over the leading `ncols` components (ncols == n for the default colorvec = 1:n)
+static fdb_status create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, int64_t ncols, const fdb_plan_opts *opts) {
   fdb_plan *P = nullptr;
   TRY(new_plan(plan, opts, m, n));
   P = *plan;
@@ -721,9 +826,9 @@ fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t 
   P->jkind = FDB_J_DENSE;
   P->ldJ = ldJ;
   // contiguous column blocks per rank
-  const int64_t per = (n + P->world - 1) / P->world;
-  P->col_begin = std::min<int64_t>(n, per * P->rank);
-  P->col_end = std::min<int64_t>(n, P->col_begin + per);
+  const int64_t per = (ncols + P->world - 1) / P->world;
+  P->col_begin = std::min<int64_t>(ncols, per * P->rank);
+  P->col_end = std::min<int64_t>(ncols, P->col_begin + per);
   const int64_t ncl = P->col_end - P->col_begin;
   P->j_len = ldJ * ncl;
   P->E = m * ncl;
@@ -749,6 +854,44 @@ fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t 
   // SURVEY.md §8(d) dense: 24*m per column
   P->alg_bytes = 24 * m * ncl;
   return FDB_OK;
+}
+
+fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const fdb_plan_opts *opts) {
+  return create_dense(plan, m, n, ldJ, n, opts);
+}
+
+// sparsity === nothing with a caller-supplied colorvec, exactly as jacobians.jl:547-557 / :589-598 / :625-631 are written:
+// `for color_i in 1:maximum(colorvec)` perturbs COMPONENT color_i (the colour id is used as an index) and writes
+// J[:, color_i]; J is not zero-filled (:530 only fills when sparsity !== nothing), so columns beyond maximum(colorvec)
+// keep their contents.  maximum(colorvec) > n indexes x1 out of bounds in the reference (BoundsError) -> FDB_ERR_INVALID.
+fdb_status fdb_plan_create_dense_colorvec(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const int64_t *colorvec,
+                                          const fdb_plan_opts *opts) {
+  if (!plan) return fail(FDB_ERR_INVALID, "plan output pointer is NULL");
+  *plan = nullptr;
+  if (!colorvec) return create_dense(plan, m, n, ldJ, n, opts);
+  if (n < 0 || m < 0) return fail(FDB_ERR_INVALID, "negative dimensions");
+  int dev = 0;
+  TRY(check_device(opts, &dev));
+  DeviceGuard g(dev);
+  long long mx = 0;
+  if (n > 0) {
+    I64View cv;
+    TRY(view_i64(colorvec, n, cv));
+    long long *d_mm = nullptr;
+    CU(cudaMalloc((void **)&d_mm, 2 * sizeof(long long)));
+    const long long init[2] = {LLONG_MIN, LLONG_MAX};
+    cudaMemcpy(d_mm, init, sizeof init, cudaMemcpyHostToDevice);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, 148 * 8));
+    color_minmax<<<blocks, kThreads>>>(cv.d, n, d_mm, d_mm + 1);
+    long long out[2] = {0, 0};
+    const cudaError_t e = cudaMemcpy(out, d_mm, sizeof out, cudaMemcpyDeviceToHost);
+    cudaFree(d_mm);
+    if (e != cudaSuccess) return fail(FDB_ERR_CUDA, "colour maximum failed: %s", cudaGetErrorString(e));
+    mx = out[0];
+  }
+  if (mx > n) return fail(FDB_ERR_INVALID, "sparsity=nothing: maximum(colorvec)=%lld indexes x beyond length(x)=%lld "
+                                           "(BoundsError in the reference, jacobians.jl:549)", mx, (long long)n);
+  return create_dense(plan, m, n, ldJ, mx < 0 ? 0 : (int64_t)mx, opts);
 }
 
 fdb_status fdb_plan_destroy(fdb_plan *plan) {
@@ -778,6 +921,24 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
   info->strategy = P->strategy;
   info->lanes = P->lanes;
   info->mean_row_jump = P->mean_row_jump;
+  {
+    // compulsory bytes of the formulation that runs (see the header); slabs read per entry: 1 (forward / complex), 2 (central)
+    const int64_t ct = P->color_bits / 8;
+    const int64_t slabs_read = P->fdtype == FDB_CENTRAL ? 2 : 1;
+    const int64_t fx_once = P->fdtype == FDB_FORWARD ? 8 * P->m : 0;
+    if (P->sp_kind == SP_CSC || P->sp_kind == SP_COO) {
+      if (P->sp_kind == SP_CSC && P->strategy == 1) {
+        const int64_t e_local = P->cm_start_h.empty() ? 0 : P->cm_start_h.back();
+        info->moved_bytes_scatter = e_local * (4 + (P->dest ? 8 : 4) + 8 * slabs_read + 8) + fx_once;
+      } else {
+        const int64_t C = std::max<int32_t>(P->C, 1);
+        const int64_t owned = P->world > 1 ? P->E * (int64_t)P->local_colors.size() / C : P->E;   // approx. share
+        info->moved_bytes_scatter = P->E * (4 + ct) * std::max<int64_t>(P->n_groups, 1) + owned * (8 * slabs_read + 8 + (P->dest ? 8 : 0)) + fx_once;
+      }
+    } else {
+      info->moved_bytes_scatter = P->alg_bytes;
+    }
+  }
   return FDB_OK;
 }
 
@@ -876,6 +1037,19 @@ struct ScatterTimer {
   }
 };
 
+// fill_matrix!(J, false) (jacobians.jl:530-532, :663).  A dense J may be a strided column-major view (ldJ > m): only
+// rows [0, m) of every column belong to J — the padding rows between the columns are not touched.
+static fdb_status zero_J(const fdb_plan *P, double *J, cudaStream_t s) {
+  if (P->jkind == FDB_J_DENSE && P->ldJ > P->m) {
+    const int64_t ncols = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : P->n;
+    if (P->m > 0 && ncols > 0)
+      CU(cudaMemset2DAsync(J, (size_t)P->ldJ * 8, 0, (size_t)P->m * 8, (size_t)ncols, s));
+    return FDB_OK;
+  }
+  CU(cudaMemsetAsync(J, 0, (size_t)P->j_len * 8, s));
+  return FDB_OK;
+}
+
 static fdb_status call_f(fdb_plan *P, fdb_fn f, void *ctx, double *fx, const double *x, int64_t batch, cudaStream_t s) {
   const int rc = f(ctx, fx, x, batch, P->ldF, P->ldx, (void *)s);
   P->cnt.f_invocations += 1;
@@ -954,7 +1128,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   //  a valid colour).  With peer buffers set the caller zero-fills J and synchronises the ranks BEFORE the call: a memset
   //  here would race with the peers' stores.
   const bool self_defining = (ident || band_data) && n_local > 0;
-  if (!self_defining && P->n_peers == 0 && P->j_len > 0) CU(cudaMemsetAsync(J, 0, (size_t)P->j_len * 8, s));
+  if (!self_defining && P->n_peers == 0 && !P->shared_J && P->j_len > 0) TRY(zero_J(P, J, s));
   if (P->ext_eps) {
     // sharded runs: the step sizes of the FULL x come from outside (fdb_color_eps on the full vector)
     if (P->C > 0) CU(cudaMemcpyAsync(P->eps, P->ext_eps, (size_t)P->C * 8, cudaMemcpyDeviceToDevice, s));
@@ -1001,55 +1175,37 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   // Double-buffered overlap (multi-GPU, column lists): group g's f! outputs live in buffer (g & 1); its scatter — the
   // kernel that also pushes the values to the peers over NVLink — runs on a side stream while the main stream already
   // evaluates group g+1 into the other buffer.  Events order buffer reuse; everything joins the caller's stream at the end.
-  const bool overlap = P->double_buffer && P->n_peers > 0 && P->side != nullptr;
+  const bool overlap = P->double_buffer && P->side != nullptr;
   const double *Fp_g = P->Fp, *Fm_g = P->Fm;
   cudaStream_t ss = s;
   auto scatter_lists = [&](int64_t g, int64_t l0, int64_t G) -> fdb_status {
-    const bool zero_bucket = g == 0 && P->rank == 0 && P->bucket_start[(size_t)P->C + 1] > P->bucket_start[(size_t)P->C];
-    int64_t li = l0;
-    bool zero_done = !zero_bucket;
-    while (li < l0 + G || !zero_done) {
-      ColScatterArgs a{};
-      a.cols = P->cols_by_color; a.colptr32 = P->colptr32; a.row = P->row32; a.dest = P->dest;
-      a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
-      a.ldF = sF;
-      int ns = 0;
-      a.seg_cum[0] = 0;
-      if (!zero_done) {
-        a.seg_start[ns] = P->bucket_start[(size_t)P->C];
-        a.seg_color[ns] = -1; a.seg_slab[ns] = 0;
-        a.seg_cum[ns + 1] = a.seg_cum[ns] + (P->bucket_start[(size_t)P->C + 1] - P->bucket_start[(size_t)P->C]);
-        ++ns;
-        zero_done = true;
-      }
-      for (; li < l0 + G && ns < kMaxSegs; ++li) {
-        const int32_t k = P->local_colors[(size_t)li];
-        a.seg_start[ns] = P->bucket_start[(size_t)k];
-        a.seg_color[ns] = k; a.seg_slab[ns] = (int32_t)(li - l0);
-        a.seg_cum[ns + 1] = a.seg_cum[ns] + (P->bucket_start[(size_t)k + 1] - P->bucket_start[(size_t)k]);
-        ++ns;
-      }
-      a.n_segs = ns;
-      const int64_t total = a.seg_cum[ns];
-      if (total == 0) continue;
-      ScatterTimer tm(P, ss);
-      auto go = [&](auto lanes_tag) {
-        constexpr int LANES = decltype(lanes_tag)::value;
-        const int64_t blocks = (total + (kThreads / LANES) - 1) / (kThreads / LANES);
-        const int grid = resident_grid(P, diff_scatter_cols<MODE, LANES>, 0, blocks);
-        diff_scatter_cols<MODE, LANES><<<grid, kThreads, 0, ss>>>(a);
-      };
-      switch (P->lanes) {
-        case 1: go(std::integral_constant<int, 1>{}); break;
-        case 2: go(std::integral_constant<int, 2>{}); break;
-        case 4: go(std::integral_constant<int, 4>{}); break;
-        case 8: go(std::integral_constant<int, 8>{}); break;
-        case 16: go(std::integral_constant<int, 16>{}); break;
-        default: go(std::integral_constant<int, 32>{}); break;
-      }
+    const bool wide = P->dest != nullptr;
+    // columns without a valid colour (rank 0, with the first group): their entries are 0
+    if (g == 0 && P->rank == 0 && P->cm_invalid_end > P->cm_start_h[(size_t)n_local]) {
+      const int64_t z0 = P->cm_start_h[(size_t)n_local], z1 = P->cm_invalid_end;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((z1 - z0 + kThreads - 1) / kThreads, (int64_t)P->sm_count * 8));
+      if (wide) zero_slots<int64_t><<<grid, kThreads, 0, ss>>>(P->cm_slot, z0, z1, J, P->d_peers, P->n_peers);
+      else zero_slots<int32_t><<<grid, kThreads, 0, ss>>>(P->cm_slot, z0, z1, J, P->d_peers, P->n_peers);
       P->cnt.kernel_launches += 1;
-      P->cnt.scatter_launches += 1;
     }
+    if (G <= 0) return FDB_OK;
+    const int64_t total = P->cm_start_h[(size_t)(l0 + G)] - P->cm_start_h[(size_t)l0];
+    if (total == 0) return FDB_OK;
+    CmArgs a{};
+    a.row = P->cm_row; a.slot = P->cm_slot; a.seg_start = P->cm_start; a.local_colors = P->d_local_colors;
+    a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
+    a.l0 = (int32_t)l0; a.G = (int32_t)G; a.ldF = sF;
+    const int64_t tiles = (total + kCmTile - 1) / kCmTile;
+    ScatterTimer tm(P, ss);
+    if (wide) {
+      const int grid = resident_grid(P, diff_scatter_cm<MODE, int64_t>, 0, tiles);
+      diff_scatter_cm<MODE, int64_t><<<grid, kThreads, 0, ss>>>(a);
+    } else {
+      const int grid = resident_grid(P, diff_scatter_cm<MODE, int32_t>, 0, tiles);
+      diff_scatter_cm<MODE, int32_t><<<grid, kThreads, 0, ss>>>(a);
+    }
+    P->cnt.kernel_launches += 1;
+    P->cnt.scatter_launches += 1;
     return FDB_OK;
   };
 
@@ -1178,7 +1334,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     for (int64_t b = 0; b < std::min<int64_t>(ng, 2); ++b) CU(cudaStreamWaitEvent(s, P->ev_scat[b], 0));
   }
   // columns without a valid colour when this rank evaluates no colour at all
-  if (n_local == 0 && P->sp_kind == SP_CSC && P->strategy == 1 && P->n_peers > 0) TRY(scatter_group(0, 0, 0));
+  if (n_local == 0 && P->sp_kind == SP_CSC && P->strategy == 1 && (P->n_peers > 0 || P->shared_J)) TRY(scatter_group(0, 0, 0));
   CU(cudaGetLastError());
   return FDB_OK;
 }
@@ -1271,8 +1427,7 @@ fdb_status fdb_jacobian(fdb_plan *P, fdb_fn f, void *ctx, const double *d_x, dou
   if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
   cudaStream_t s = (cudaStream_t)stream;
   // jacobians.jl:508-509 defaults
-  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);
-  if (!(absstep > 0)) absstep = relstep;
+  resolve_steps(P->fdtype, relstep, absstep);
   double *fx = d_fx ? d_fx : P->fx_own;
   fdb_status st;
   if (P->use_graph && !P->timing) {
@@ -1322,7 +1477,7 @@ fdb_status fdb_jacobian_complex(fdb_plan *P, fdb_fn_c f, void *ctx, const double
   if (P->fdtype != FDB_COMPLEX) return fail(FDB_ERR_INVALID, "fdb_jacobian_complex needs a plan created with fdtype = FDB_COMPLEX");
   // same C signature up to the element type of the buffers: the complex128 slabs are handed over as raw pointers
   P->complex_entry = true;
-  const fdb_status st = fdb_jacobian(P, reinterpret_cast<fdb_fn>(f), ctx, d_x, d_J, nullptr, nullptr, 0.0, 0.0, 1.0, stream);
+  const fdb_status st = fdb_jacobian(P, reinterpret_cast<fdb_fn>(f), ctx, d_x, d_J, nullptr, nullptr, FDB_STEP_DEFAULT, FDB_STEP_DEFAULT, 1.0, stream);
   P->complex_entry = false;
   return st;
 }
@@ -1350,8 +1505,7 @@ fdb_status fdb_color_eps(fdb_plan *P, const double *d_x, double relstep, double 
   DeviceGuard g(P->device);
   if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);
-  if (!(absstep > 0)) absstep = relstep;
+  resolve_steps(P->fdtype, relstep, absstep);
   TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
     using CT = decltype(tag);
     return run_eps<CT>(P, d_x, relstep, absstep, dir, s);
@@ -1403,8 +1557,7 @@ fdb_status fdb_jvp(fdb_plan *P, fdb_fn f, void *ctx, double *d_jvp, const double
   DeviceGuard g(P->device);
   if (!g.ok) return fail(FDB_ERR_CUDA, "cannot select device %d", P->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!(relstep > 0)) relstep = fdb_default_relstep(P->fdtype);     // jvp.jl:245-246
-  if (!(absstep > 0)) absstep = relstep;
+  resolve_steps(P->fdtype, relstep, absstep);                       // jvp.jl:245-246
   double *x1 = d_x1 ? d_x1 : P->xp;
   double *fx1 = d_fx1 ? d_fx1 : P->fx_own;
   const bool central = P->fdtype == FDB_CENTRAL;
@@ -1456,7 +1609,17 @@ fdb_status fdb_jacobian_host(fdb_plan *P, fdb_fn f, void *ctx, const double *h_x
   }
   fdb_status st = fdb_jacobian(P, f, ctx, P->h_dx, P->h_dJ, P->h_dfx, fin, relstep, absstep, dir, (void *)s);
   if (st != FDB_OK) { cudaStreamSynchronize(s); return st; }
-  if (P->j_len > 0) CU(cudaMemcpyAsync(h_J, P->h_dJ, (size_t)P->j_len * 8, cudaMemcpyDeviceToHost, s));
+  if (P->j_len > 0) {
+    if (P->jkind == FDB_J_DENSE && P->ldJ > P->m) {
+      // strided dense view: only rows [0, m) of each column are J's (the host padding rows stay untouched)
+      const int64_t ncols = P->sp_kind == SP_NONE ? P->col_end - P->col_begin : P->n;
+      if (P->m > 0 && ncols > 0)
+        CU(cudaMemcpy2DAsync(h_J, (size_t)P->ldJ * 8, P->h_dJ, (size_t)P->ldJ * 8, (size_t)P->m * 8, (size_t)ncols,
+                             cudaMemcpyDeviceToHost, s));
+    } else {
+      CU(cudaMemcpyAsync(h_J, P->h_dJ, (size_t)P->j_len * 8, cudaMemcpyDeviceToHost, s));
+    }
+  }
   if (h_fx && P->fdtype == FDB_FORWARD && !fin && P->m > 0)
     CU(cudaMemcpyAsync(h_fx, P->h_dfx, (size_t)P->m * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -1502,3 +1665,5 @@ fdb_status fdb_ipc_open(const unsigned char handle[64], void **d_ptr) {
 fdb_status fdb_ipc_close(void *d_ptr) { CU(cudaIpcCloseMemHandle(d_ptr)); return FDB_OK; }
 
 }  // extern "C"
+
+#include "fdjac_group.cuh"

@@ -256,6 +256,38 @@ bucket_columns(const CT *__restrict__ jcolor, int64_t n, int32_t C, unsigned lon
   }
 }
 
+// ---- colour-major entry lists (diff_scatter_cm) ----
+// list_cols[i] = i-th column of this rank's colour-major order (its local colours one after the other, then — rank 0
+// only — the columns without a valid colour); list_cnt[i] = stored entries of that column.
+__global__ void __launch_bounds__(kThreads)
+cm_column_counts(const int32_t *__restrict__ list_cols, int64_t ncols, const int32_t *__restrict__ colptr32,
+                 int32_t *__restrict__ list_cnt) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < ncols; i += stride) {
+    const int32_t c = list_cols[i];
+    list_cnt[i] = colptr32[c + 1] - colptr32[c];
+  }
+}
+
+// cm_row / cm_slot from the exclusive scan of list_cnt: column i's entries land at [off[i], off[i] + cnt)
+template <typename ST>
+__global__ void __launch_bounds__(kThreads)
+cm_expand(const int32_t *__restrict__ list_cols, const int32_t *__restrict__ list_off, int64_t ncols,
+          const int32_t *__restrict__ colptr32, const int32_t *__restrict__ row32, const int64_t *__restrict__ dest,
+          int lanes, int32_t *__restrict__ cm_row, ST *__restrict__ cm_slot) {
+  const int cols_per_block = kThreads / lanes;
+  const int sub = threadIdx.x % lanes;
+  for (int64_t i = blockIdx.x * (int64_t)cols_per_block + threadIdx.x / lanes; i < ncols; i += (int64_t)gridDim.x * cols_per_block) {
+    const int32_t c = list_cols[i];
+    const int32_t p0 = colptr32[c], p1 = colptr32[c + 1];
+    const int64_t q0 = list_off[i];
+    for (int32_t p = p0 + sub; p < p1; p += lanes) {
+      cm_row[q0 + (p - p0)] = row32[p];
+      cm_slot[q0 + (p - p0)] = dest ? (ST)dest[p] : (ST)p;
+    }
+  }
+}
+
 // Step-size plan aid: in which aligned lane groups of g = 2,4,8,16,32 consecutive columns does a colour repeat?
 // bit log2(g) of *flags is set when some aligned g-group holds two columns of the same valid colour.  The window
 // sum-of-squares kernel lets the lanes of a conflict-free group update their shared-memory accumulators without any

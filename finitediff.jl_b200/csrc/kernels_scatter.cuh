@@ -203,51 +203,91 @@ diff_scatter_dest(const ScatterArgs a) {
   }
 }
 
-// ---- per-colour column-list scatter (CSC) ----
+// ---- colour-major entry lists (CSC) ----
 // The literal shape of ext/FiniteDiffSparseArraysExt.jl:38-47 — "for every column of colour k, for every stored entry:
-// nzval[p] = vfx[rowval[p]]" — driven by the per-colour column lists built at plan time, LANES lanes per column.
-// Used when a launch would otherwise stream entries it does not own: colours sharded over GPUs (a rank touches only
-// the columns of its colours; the stores to the peers ride in the same kernel) or more colours than resident slabs.
-constexpr int kMaxSegs = 8;
-struct ColScatterArgs {
-  const int32_t *cols;       // cols_by_color
-  const int32_t *colptr32;   // [n+1] 0-based
-  const int32_t *row;        // [E]
-  const int64_t *dest;       // [E] or null
+// nzval[p] = vfx[rowval[p]]" — with the column test and the colptr walk done ONCE, at plan time: the entries of the
+// colours this rank evaluates are laid out colour by colour (local colour order), column by column inside a colour, as
+// two coalesced streams  cm_row[q] (row of the entry)  and  cm_slot[q] (where its value goes in J).  A launch covers the
+// contiguous range of one GROUP of colours (those whose f! outputs are resident), so it only ever streams entries it
+// owns: this is the form used when colours are sharded over GPUs (the stores to the peers ride in the same kernel) and
+// when there are more colours than resident slabs (the slab is gathered while it is still in L2).
+// Dependent-load depth is 2 (index stream -> slab gather); r1's per-column form walked cols -> colptr -> row -> slab
+// (depth 4) and ran at 0.10 of the HBM roofline, one launch per colour.
+struct CmArgs {
+  const int32_t *row;          // [E_local] colour-major
+  const void *slot;            // [E_local] int32 (nzval slot) or int64 (explicit destination)
+  const int64_t *seg_start;    // [n_local + 1] first entry of every local colour
+  const int32_t *local_colors; // [n_local] global colour id of every local colour
   const double *fx, *Fp, *Fm, *eps;
   double *J;
   double *const *peers;
-  int32_t n_peers, n_segs;
+  int32_t n_peers;
+  int32_t l0, G;               // this launch: local colours [l0, l0+G); slab of local colour li is li - l0
   int64_t ldF;
-  int64_t seg_start[kMaxSegs];   // offset of the segment in cols
-  int64_t seg_cum[kMaxSegs + 1]; // cumulative column counts of the launch's segments
-  int32_t seg_color[kMaxSegs];   // global colour (for eps), or -1: columns without a valid colour -> zeros
-  int32_t seg_slab[kMaxSegs];    // slab index of the colour's f! output
 };
 
-template <int MODE, int LANES>
+constexpr int kCmMaxGroup = 1024;          // colours per launch whose (start, eps) tables fit the static shared arrays
+constexpr int kCmPerThread = 4;
+constexpr int kCmTile = kThreads * kCmPerThread;
+
+template <int MODE, typename ST>
 __global__ void __launch_bounds__(kThreads)
-diff_scatter_cols(const ColScatterArgs a) {
-  constexpr int kColsPerBlock = kThreads / LANES;
-  const int sub = threadIdx.x % LANES;
-  const int64_t total = a.seg_cum[a.n_segs];
-  for (int64_t i = blockIdx.x * (int64_t)kColsPerBlock + threadIdx.x / LANES; i < total; i += (int64_t)gridDim.x * kColsPerBlock) {
-    int s = 0;
+diff_scatter_cm(const CmArgs a) {
+  __shared__ int64_t s_start[kCmMaxGroup + 1];
+  __shared__ double s_eps[kCmMaxGroup];
+  for (int i = threadIdx.x; i <= a.G; i += kThreads) s_start[i] = a.seg_start[a.l0 + i];
+  for (int i = threadIdx.x; i < a.G; i += kThreads) s_eps[i] = a.eps[a.local_colors[a.l0 + i]];
+  __syncthreads();
+  const ST *__restrict__ slot = reinterpret_cast<const ST *>(a.slot);
+  const int64_t q0 = s_start[0], q1 = s_start[a.G];
+  for (int64_t tile = q0 + (int64_t)blockIdx.x * kCmTile; tile < q1; tile += (int64_t)gridDim.x * kCmTile) {
+    int32_t r[kCmPerThread];
+    ST d[kCmPerThread];
 #pragma unroll
-    for (int q = 1; q < kMaxSegs; ++q) s += (q < a.n_segs && i >= a.seg_cum[q]) ? 1 : 0;
-    const int32_t c = __ldg(a.cols + a.seg_start[s] + (i - a.seg_cum[s]));
-    const int32_t k = a.seg_color[s];
-    const int32_t p0 = __ldg(a.colptr32 + c), p1 = __ldg(a.colptr32 + c + 1);
-    const double e = k >= 0 ? __ldg(a.eps + k) : 1.0;
-    const double *hi = a.Fp + (int64_t)a.seg_slab[s] * a.ldF;
-    const double *lo = MODE == kCentral ? a.Fm + (int64_t)a.seg_slab[s] * a.ldF : a.fx;
-    for (int32_t p = p0 + sub; p < p1; p += LANES) {
-      double v = 0.0;
-      if (k >= 0) v = fd_quotient<MODE>(hi, lo, __ldg(a.row + p), e);   // fused with ext/..SparseArraysExt.jl:44
-      const int64_t d = a.dest ? __ldg(a.dest + p) : (int64_t)p;
-      a.J[d] = v;
-      for (int q = 0; q < a.n_peers; ++q) a.peers[q][d] = v;
+    for (int u = 0; u < kCmPerThread; ++u) {
+      const int64_t q = tile + u * kThreads + threadIdx.x;
+      r[u] = 0; d[u] = 0;
+      if (q < q1) { r[u] = __ldcs(a.row + q); d[u] = __ldcs(slot + q); }
     }
+    // segment of the tile's first entry (uniform binary search), then at most a few steps forward per entry
+    int seg = 0;
+    {
+      int lo = 0, hi = a.G;   // s_start[lo] <= tile < s_start[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_start[mid] <= tile) lo = mid; else hi = mid; }
+      seg = lo;
+    }
+    double v[kCmPerThread];
+#pragma unroll
+    for (int u = 0; u < kCmPerThread; ++u) {
+      const int64_t q = tile + u * kThreads + threadIdx.x;
+      v[u] = 0.0;
+      if (q < q1) {
+        while (q >= s_start[seg + 1]) ++seg;
+        const double *hi_p = a.Fp + (int64_t)seg * a.ldF;
+        const double *lo_p = MODE == kCentral ? a.Fm + (int64_t)seg * a.ldF : a.fx;
+        v[u] = fd_quotient<MODE>(hi_p, lo_p, r[u], s_eps[seg]);            // fused with ext/..SparseArraysExt.jl:44
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kCmPerThread; ++u) {
+      const int64_t q = tile + u * kThreads + threadIdx.x;
+      if (q < q1) {
+        a.J[d[u]] = v[u];
+        for (int p = 0; p < a.n_peers; ++p) a.peers[p][d[u]] = v[u];
+      }
+    }
+  }
+}
+
+// columns without a valid colour (colorvec[col] < 1): their entries stay 0 (fill_matrix! semantics); rank 0 writes them
+template <typename ST>
+__global__ void __launch_bounds__(kThreads)
+zero_slots(const void *slot_v, int64_t q0, int64_t q1, double *__restrict__ J, double *const *peers, int32_t n_peers) {
+  const ST *__restrict__ slot = reinterpret_cast<const ST *>(slot_v);
+  for (int64_t q = q0 + blockIdx.x * (int64_t)kThreads + threadIdx.x; q < q1; q += (int64_t)gridDim.x * kThreads) {
+    const int64_t d = slot[q];
+    J[d] = 0.0;
+    for (int p = 0; p < n_peers; ++p) peers[p][d] = 0.0;
   }
 }
 

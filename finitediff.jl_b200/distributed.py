@@ -114,31 +114,208 @@ class IpcBuffer:
             self.ptr = 0
 
 
+class DeviceBarrier:
+    """fdb_sync: the device-side barrier that orders one-process-per-GPU ranks without NCCL on the data path — a flag
+    block per rank in peer memory (CUDA IPC), one tiny kernel per barrier enqueued on the caller's stream
+    (st.release.sys to every peer, ld.acquire.sys until every peer has signalled).  torch.distributed is used once, at
+    construction, to exchange the 64-byte IPC handles."""
+
+    def __init__(self, device, group=None):
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().fdb_sync_create(C.byref(h), self.rank, self.world, api._device_index(self.device)))
+        self._h = h
+        flags = C.c_void_p()
+        L.check(L.lib().fdb_sync_flags(self._h, C.byref(flags)))
+        mine = C.create_string_buffer(64)
+        L.check(L.lib().fdb_ipc_get_handle(flags, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.raw, group=group)
+        self._mapped = []
+        ptrs = (C.c_void_p * self.world)()
+        with torch.cuda.device(self.device):
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    ptrs[r] = flags.value
+                    continue
+                p = C.c_void_p()
+                L.check(L.lib().fdb_ipc_open(hb, C.byref(p)))
+                self._mapped.append(p.value)
+                ptrs[r] = p.value
+            L.check(L.lib().fdb_sync_set_peers(self._h, ptrs))
+        dist.barrier(group=group)          # every rank has mapped every flag block before the first signal
+
+    def wait(self, stream=None):
+        """Enqueue one barrier on `stream` (default: the current stream of the device)."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(L.lib().fdb_sync_barrier(self._h, C.c_void_p(stream)))
+
+    def close(self):
+        if self._h is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._mapped:
+                L.lib().fdb_ipc_close(C.c_void_p(p))
+            self._mapped = []
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        L.lib().fdb_sync_destroy(self._h)
+        self._h = None
+
+
+class GroupJacobian:
+    """ONE process driving several GPUs through fdb_group_* (the C ABI's own multi-GPU entry: no torch.distributed, no
+    NCCL): colours (dense: column blocks) are partitioned over `devices`; devices[0] is the root and owns x, J and fx;
+    every member's scatter kernel stores the entries it owns straight into the root's J over NVLink.  Device ordinals
+    may repeat ([0, 0] runs two members on one GPU — the same code path on a single-GPU box).
+
+    fs: one f! per member (NativeFn whose context lives on that member's device, or a Python callable)."""
+
+    def __init__(self, J, colorvec, fdtype, devices, *, sparsity=api._DEFAULT, **plan_kw):
+        self.devices = [api._device_index(d) if not isinstance(d, int) else int(d) for d in devices]
+        self.root = torch.device("cuda", self.devices[0])
+        self.J, self.fdtype = J, fdtype
+        if sparsity is api._DEFAULT:
+            sparsity = J if api._has_sparsestruct(J) else None
+        fd = api._fdtype_code(fdtype)
+        o = api._opts(fd, self.devices[0], **plan_kw)
+        n_dev = len(self.devices)
+        devs = (C.c_int * n_dev)(*self.devices)
+        h = C.c_void_p()
+        cv_ptr, k0 = api._index_ptr(colorvec)
+        self._keep = [k0]
+        lib = L.lib()
+        if sparsity is None:
+            m, n, ld = api._dense_ld(J)
+            L.check(lib.fdb_group_create_dense(C.byref(h), n_dev, devs, m, n, ld, C.byref(o)))
+        elif isinstance(sparsity, api.SparseMatrixCSC):
+            cp, k1 = api._index_ptr(sparsity.colptr)
+            rv, k2 = api._index_ptr(sparsity.rowval)
+            self._keep += [k1, k2]
+            if isinstance(J, api.SparseMatrixCSC):
+                same = J is sparsity or (J.colptr is sparsity.colptr and J.rowval is sparsity.rowval)
+                jcp = jrv = None
+                if not same:
+                    jcp, k3 = api._index_ptr(J.colptr)
+                    jrv, k4 = api._index_ptr(J.rowval)
+                    self._keep += [k3, k4]
+                L.check(lib.fdb_group_create_csc(C.byref(h), n_dev, devs, sparsity.m, sparsity.n, cp, rv, L.FDB_J_CSC_NZVAL,
+                                                 jcp, jrv, 0, cv_ptr, C.byref(o)))
+            else:
+                m, n, ld = api._dense_ld(J)
+                L.check(lib.fdb_group_create_csc(C.byref(h), n_dev, devs, m, n, cp, rv, L.FDB_J_DENSE, None, None, ld,
+                                                 cv_ptr, C.byref(o)))
+        elif isinstance(sparsity, api.BandedMatrix):
+            if isinstance(J, api.BandedMatrix):
+                L.check(lib.fdb_group_create_banded(C.byref(h), n_dev, devs, sparsity.m, sparsity.n, sparsity.l, sparsity.u,
+                                                    L.FDB_J_BAND, 0, cv_ptr, C.byref(o)))
+            else:
+                m, n, ld = api._dense_ld(J)
+                L.check(lib.fdb_group_create_banded(C.byref(h), n_dev, devs, m, n, sparsity.l, sparsity.u, L.FDB_J_DENSE, ld,
+                                                    cv_ptr, C.byref(o)))
+        else:
+            raise TypeError(f"GroupJacobian: unsupported sparsity type {type(sparsity)}")
+        self._h = h
+        self._fin = api.weakref.finalize(self, lib.fdb_group_destroy, C.c_void_p(h.value))
+        self.plans = []
+        for i in range(n_dev):
+            p = C.c_void_p()
+            L.check(lib.fdb_group_plan(self._h, i, C.byref(p)))
+            self.plans.append(api.Plan(p.value, owned=False))
+        self._fns = None
+
+    def run(self, fs, x, fx=None, f_in=None, *, relstep=None, absstep=None, dir=True, stream=None):
+        m, n = api._shape_of(self.J)
+        if len(fs) != len(self.devices):
+            raise ValueError("one f! per member")
+        if self._fns is None or self._fns[0] is not fs:
+            if all(isinstance(f, api.NativeFn) for f in fs):
+                wrapped = [api._as_fn(f, m, n, torch.device("cuda", d), 1) for f, d in zip(fs, self.devices)]
+            else:
+                # Python callables: ONE trampoline (the ABI takes one f and a context per member); the context is the
+                # member index + 1, the trampoline forwards to that member's wrapper (tensors on that member's device)
+                per = [api._PyFn(f, m, n, torch.device("cuda", d), bool(getattr(f, "batched", False))) for f, d in zip(fs, self.devices)]
+
+                def tramp(ctx, p_fx, p_x, batch, ldfx, ldx, stream, _per=per):
+                    return _per[int(ctx or 1) - 1]._tramp(None, p_fx, p_x, batch, ldfx, ldx, stream)
+
+                cf = L.FDB_FN(tramp)
+                wrapped = [(L.fn_address(cf), C.c_void_p(i + 1), per[i]) for i in range(len(per))]
+                self._tramp_keep = cf
+            self._fns = (fs, wrapped)
+        wrapped = self._fns[1]
+        addr = wrapped[0][0]
+        if any(w[0] != addr for w in wrapped):
+            raise ValueError("all members must share one f! entry point (contexts may differ per device)")
+        ctxs = (C.c_void_p * len(wrapped))(*[C.cast(w[1], C.c_void_p).value if w[1] is not None else None for w in wrapped])
+        if stream is None:
+            stream = torch.cuda.current_stream(self.root).cuda_stream
+        jv = api._j_values(self.J)
+        with torch.cuda.device(self.root):
+            st = L.lib().fdb_group_jacobian(self._h, addr, ctxs, x.data_ptr(), jv.data_ptr(),
+                                            None if fx is None else fx.data_ptr(), None if f_in is None else f_in.data_ptr(),
+                                            L.STEP_DEFAULT if relstep is None else float(relstep),
+                                            L.STEP_DEFAULT if absstep is None else float(absstep), float(dir), C.c_void_p(stream))
+        for w in wrapped:
+            if st == L.FDB_ERR_CALLBACK and w[2] is not None and w[2].exc is not None:
+                exc, w[2].exc = w[2].exc, None
+                raise exc
+        L.check(st)
+
+    def synchronize(self):
+        for d in set(self.devices):
+            torch.cuda.synchronize(d)
+
+    def close(self):
+        self.synchronize()
+        self._fin()
+
+
 class ShardedJacobian:
     """finite_difference_jacobian! with the colours of `cache.colorvec` sharded over the ranks of the default process
-    group (the cache must have been built with rank=, world=).  After run() every rank holds the complete J."""
+    group, one process per GPU (the cache must have been built with rank=, world=).
+
+    mode="p2p" (default): no collective on the data path.  Rank 0's nzval lives in a CUDA-IPC buffer that every rank
+    maps; the plans are created with shared_j, so each rank's diff+scatter kernel stores the entries it owns STRAIGHT
+    into rank 0's nzval over NVLink (the literal "final gather of Jacobian columns", fused into the kernel), and the
+    ranks are ordered by the device-side flag barrier of the C ABI (fdb_sync: DeviceBarrier) — no NCCL call per Jacobian.
+      gather="root"     rank 0 ends with the complete J;
+      gather="all"      + one NCCL broadcast of nzval (bulk, full NVLink bandwidth): every rank ends with it;
+      gather="all_p2p"  every value is stored to EVERY peer by the scatter kernel (fdb_plan_set_peers).  Fine up to 4
+                        GPUs, 16 ms at 8 (7 peer apertures x scattered 64-byte runs) — kept for experiments only.
+    mode="nccl": pack owned entries -> all_gather -> unpack (fallback; also what the CPU/gloo tests exercise)."""
 
     def __init__(self, J: api.SparseMatrixCSC, cache: api.JacobianCache, n: int, device, mode: str = "p2p", group=None,
-                 pre_sync: bool = True, gather: str = "all"):
-        """gather="root": rank 0 ends with the complete J — every rank's scatter kernel stores its values straight into
-        rank 0's nzval (the literal "final gather of Jacobian columns");
-        gather="all": every rank does: the same fused gather to rank 0, then one NCCL broadcast of nzval (bulk, full
-        NVLink bandwidth);
-        gather="all_p2p": every value is stored to EVERY peer by the scatter kernel.  Fine up to 4 GPUs (3.35x at 4), but
-        measured 16 ms at 8 GPUs (7 peer apertures x scattered 64-byte runs) — kept for experiments only."""
+                 pre_sync: bool = True, gather: str = "all", barrier: str = "device"):
         if gather not in ("all", "root", "all_p2p"):
             raise ValueError("gather must be 'all', 'root' or 'all_p2p'")
+        if barrier not in ("device", "nccl"):
+            raise ValueError("barrier must be 'device' (fdb_sync) or 'nccl' (all_reduce of a flag word)")
         self.gather = gather
         if not isinstance(J, api.SparseMatrixCSC):
-            raise TypeError("ShardedJacobian shards CSC Jacobians (dense plans shard columns: Plan.dense_range())")
+            raise TypeError("ShardedJacobian shards CSC Jacobians (dense / banded plans: GroupJacobian, or rank/world plans "
+                            "with their own column slabs)")
         self.J, self.cache, self.n, self.device, self.group = J, cache, n, torch.device(device), group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.pre_sync = pre_sync
+        self.shared = mode == "p2p" and gather in ("root", "all")
+        if self.shared:
+            cache._plan_kw["shared_j"] = True
         self.plan = cache.plan_for(J, cache.sparsity, cache.colorvec, n)
         self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.mode = mode
         self._peers = []
+        self._root_ptr = None
+        self._J_run = J
         self._ipc: Optional[IpcBuffer] = None
+        self.barrier: Optional[DeviceBarrier] = None
+        self._barrier_kind = barrier
         if mode == "p2p":
             try:
                 self._setup_p2p()
@@ -153,30 +330,54 @@ class ShardedJacobian:
 
     def _setup_p2p(self):
         nnz = self.J.nzval.numel()
-        self._ipc = IpcBuffer(nnz, self.device)
-        self._ipc.tensor.copy_(self.J.nzval)
-        self.J.nzval = self._ipc.tensor                 # J's values now live in the IPC-exportable buffer
         handles = [None] * self.world
-        dist.all_gather_object(handles, self._ipc.handle(), group=self.group)
-        ptrs = []
-        with torch.cuda.device(self.device):
-            for r, h in enumerate(handles):
-                if r == self.rank or (self.gather != "all_p2p" and (r != 0 or self.rank == 0)):
-                    continue
+        if self.shared:
+            mine = None
+            if self.rank == 0:
+                self._ipc = IpcBuffer(nnz, self.device)
+                self._ipc.tensor.copy_(self.J.nzval)
+                self.J.nzval = self._ipc.tensor             # rank 0's values now live in the IPC-exportable buffer
+                mine = self._ipc.handle()
+            dist.all_gather_object(handles, mine, group=self.group)
+            if self.rank != 0:
                 p = C.c_void_p()
-                L.check(L.lib().fdb_ipc_open(h, C.byref(p)))
-                ptrs.append(p.value)
-        self._peers = ptrs
-        self.plan.set_peers(ptrs)
+                with torch.cuda.device(self.device):
+                    L.check(L.lib().fdb_ipc_open(handles[0], C.byref(p)))
+                self._root_ptr = p.value
+                root_vals = torch.as_tensor(api._DevArray(self._root_ptr, (nnz,)), device=self.device)
+                self._J_run = api.SparseMatrixCSC(self.J.m, self.J.n, self.J.colptr, self.J.rowval, root_vals)
+        else:
+            self._ipc = IpcBuffer(nnz, self.device)
+            self._ipc.tensor.copy_(self.J.nzval)
+            self.J.nzval = self._ipc.tensor
+            dist.all_gather_object(handles, self._ipc.handle(), group=self.group)
+            ptrs = []
+            with torch.cuda.device(self.device):
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    p = C.c_void_p()
+                    L.check(L.lib().fdb_ipc_open(h, C.byref(p)))
+                    ptrs.append(p.value)
+            self._peers = ptrs
+            self.plan.set_peers(ptrs)
+        if self._barrier_kind == "device":
+            self.barrier = DeviceBarrier(self.device, self.group)
         ok = torch.ones(1, device=self.device)
         dist.all_reduce(ok, group=self.group)
 
+    def _sync(self):
+        if self.barrier is not None:
+            self.barrier.wait()
+        else:
+            dist.all_reduce(self.flag, group=self.group)
+
     def run(self, f, x, **kw):
         if self.mode == "p2p" and self.pre_sync:
-            dist.all_reduce(self.flag, group=self.group)    # nobody may still be reading J (stream-ordered)
-        api.finite_difference_jacobian_(self.J, f, x, self.cache, **kw)
+            self._sync()                                   # nobody may still be reading J (stream-ordered)
+        api.finite_difference_jacobian_(self._J_run, f, x, self.cache, **kw)
         if self.mode == "p2p":
-            dist.all_reduce(self.flag, group=self.group)    # every rank's scatter (incl. its peer stores) has completed
+            self._sync()                                   # every rank's scatter (incl. its NVLink stores) has completed
             if self.gather == "all":
                 dist.broadcast(self.J.nzval, src=0, group=self.group)
         else:
@@ -184,13 +385,21 @@ class ShardedJacobian:
         return None
 
     def close(self):
+        torch.cuda.synchronize(self.device)
         if self._peers:
             self.plan.set_peers([])
             with torch.cuda.device(self.device):
                 for p in self._peers:
                     L.lib().fdb_ipc_close(C.c_void_p(p))
             self._peers = []
-        torch.cuda.synchronize(self.device)
+        if self._root_ptr:
+            with torch.cuda.device(self.device):
+                L.lib().fdb_ipc_close(C.c_void_p(self._root_ptr))
+            self._root_ptr = None
+            self._J_run = self.J
+        if self.barrier is not None:
+            self.barrier.close()
+            self.barrier = None
         if self.group is None or dist.is_initialized():
             try:
                 dist.barrier(group=self.group)
@@ -267,8 +476,8 @@ class EpsPlan:
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            L.check(L.lib().fdb_color_eps(self.plan.handle, x.data_ptr(), 0.0 if relstep is None else float(relstep),
-                                          0.0 if absstep is None else float(absstep), float(dir), self.eps.data_ptr(),
+            L.check(L.lib().fdb_color_eps(self.plan.handle, x.data_ptr(), L.STEP_DEFAULT if relstep is None else float(relstep),
+                                          L.STEP_DEFAULT if absstep is None else float(absstep), float(dir), self.eps.data_ptr(),
                                           C.c_void_p(stream)))
         return self.eps
 
@@ -314,7 +523,7 @@ class ColumnBlockJacobian:
         base = self.values_default.data_ptr() if values_ptr is None else int(values_ptr)
         with torch.cuda.device(self.device):
             st = L.lib().fdb_jacobian(self.plan.handle, addr, ctx, x.data_ptr() + 8 * self.x0, base + 8 * self.p0, None,
-                                      None, 0.0, 0.0, float(dir), C.c_void_p(stream))
+                                      None, L.STEP_DEFAULT, L.STEP_DEFAULT, float(dir), C.c_void_p(stream))
         if st == L.FDB_ERR_CALLBACK and pyfn is not None and pyfn.exc is not None:
             exc, pyfn.exc = pyfn.exc, None
             raise exc
@@ -339,7 +548,9 @@ class ColumnShardedJacobian:
         self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._ipc: Optional[IpcBuffer] = None
         self._root_ptr = None
+        self.barrier: Optional[DeviceBarrier] = None
         if gather == "root":
+            self.barrier = DeviceBarrier(self.device, group)
             handles = [None] * self.world
             mine = None
             if self.rank == 0:
@@ -358,10 +569,10 @@ class ColumnShardedJacobian:
     def run(self, x: torch.Tensor, dir=True):
         eps = self.eps_plan.compute(x, dir=dir)
         if self.gather == "root":
-            dist.all_reduce(self.flag, group=self.group)      # rank 0 is done reading the previous J
+            self.barrier.wait()                               # rank 0 is done reading the previous J
         self.block.run(x, eps, values_ptr=self._root_ptr, dir=dir)
         if self.gather == "root":
-            dist.all_reduce(self.flag, group=self.group)      # every block (incl. its peer stores) has completed
+            self.barrier.wait()                               # every block (incl. its NVLink stores) has completed
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -369,6 +580,9 @@ class ColumnShardedJacobian:
             with torch.cuda.device(self.device):
                 L.lib().fdb_ipc_close(C.c_void_p(self._root_ptr))
             self._root_ptr = None
+        if self.barrier is not None:
+            self.barrier.close()
+            self.barrier = None
         try:
             dist.barrier(group=self.group)
         except Exception:

@@ -29,7 +29,12 @@
 extern "C" {
 #endif
 
-#define FDB_ABI_VERSION 1
+#define FDB_ABI_VERSION 2
+
+/* "keyword not given" for relstep / absstep (jacobians.jl:508-510 defaults: relstep = default_relstep(fdtype, T),
+ * absstep = relstep).  Any other value, 0 included, is used as passed: relstep = 0 is a pure absolute step,
+ * absstep = 0 a pure relative one, as in the reference. */
+#define FDB_STEP_DEFAULT (__builtin_nan(""))
 
 typedef enum {
   FDB_OK = 0,
@@ -86,7 +91,10 @@ typedef struct {
   int32_t use_graph;       /* 1: capture the whole call (library kernels + the callback's launches) into a CUDA graph on
                               first use and replay it while (f, ctx, buffers, scalars) stay the same.  The callback must
                               be capture-safe: enqueue-only on the given stream, no allocation, no host-side state. */
-  int32_t reserved;
+  int32_t shared_j;        /* 1: the J passed to fdb_jacobian is SHARED with other ranks' plans (a peer-mapped pointer to one
+                              buffer, e.g. rank 0's): this plan only stores the entries / columns it owns and never zero-fills
+                              J — the owner of the buffer zero-fills it (when the scatter is not self-defining) and orders
+                              the ranks (fdb_sync_barrier / fdb_group_jacobian do both) */
 } fdb_plan_opts;
 
 typedef struct fdb_plan fdb_plan;
@@ -106,6 +114,10 @@ typedef struct {
   int32_t strategy;        /* chosen scatter strategy: 0 fused single pass, 1 per-colour column lists */
   int32_t lanes;           /* lanes per column of the column-list kernel */
   double mean_row_jump;    /* mean |row[e+1]-row[e]| over consecutive entries (gather locality metric) */
+  int64_t moved_bytes_scatter; /* COMPULSORY bytes of the shipped diff+scatter formulation per Jacobian (this rank): every
+                              index / slab / fx / J byte it must move once — the roofline numerator.  CSC fused pass:
+                              E*(4 + |colour| + 8*slabs_read + 8) [+ 8m fx, forward]; colour-major lists: E*(4 + |slot| +
+                              8*slabs_read + 8) [+ 8m]; explicit destinations: + 8 per entry; banded / dense: = alg_bytes */
 } fdb_plan_info_t;
 
 typedef struct {
@@ -156,6 +168,11 @@ fdb_status fdb_plan_create_banded(fdb_plan **plan, int64_t m, int64_t n, int64_t
  * With world>1 the columns are block-partitioned: this rank computes columns [col_begin, col_end) (0-based, see
  * fdb_plan_info) and d_J passed to fdb_jacobian points at THAT column slab (ldJ x ncols_local). */
 fdb_status fdb_plan_create_dense(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const fdb_plan_opts *opts);
+/* sparsity === nothing WITH a caller-supplied colorvec, as jacobians.jl:547-557 is written: the loop runs color_i in
+ * 1:maximum(colorvec), perturbs COMPONENT color_i and writes J[:, color_i] (J is not zero-filled; later columns keep
+ * their contents).  maximum(colorvec) > n (BoundsError in the reference) => FDB_ERR_INVALID.  colorvec NULL => 1:n. */
+fdb_status fdb_plan_create_dense_colorvec(fdb_plan **plan, int64_t m, int64_t n, int64_t ldJ, const int64_t *colorvec,
+                                          const fdb_plan_opts *opts);
 
 fdb_status fdb_plan_destroy(fdb_plan *plan);
 fdb_status fdb_plan_info(const fdb_plan *plan, fdb_plan_info_t *info);
@@ -187,7 +204,7 @@ fdb_status fdb_plan_read_timing(fdb_plan *plan, double *scatter_ms, int64_t *sca
  *   d_fx   : m doubles (device) — cache.fx.  Forward mode: receives f(x) unless d_f_in is given.  May be NULL
  *            (plan-owned buffer is used).  Central mode: unused.
  *   d_f_in : forward mode only: precomputed f(x) (`f_in`, jacobians.jl:540-545) or NULL.
- *   relstep, absstep: <= 0 => defaults (default_relstep(fdtype); absstep = relstep).
+ *   relstep, absstep: FDB_STEP_DEFAULT (NaN) => defaults (default_relstep(fdtype); absstep = relstep); other values as passed.
  *   dir    : forward only (epsilons.jl:28); pass 1.0 for the default `dir=true`.
  *   stream : cudaStream_t (NULL = legacy default stream).
  * f!-call count and order match the reference: forward f(x) first (unless f_in) then colours ascending;
@@ -224,6 +241,49 @@ fdb_status fdb_eps_plan_create(fdb_plan **plan, int64_t n, const int64_t *colorv
 fdb_status fdb_color_eps(fdb_plan *plan, const double *d_x, double relstep, double absstep, double dir,
                          double *d_eps_out, void *stream);
 fdb_status fdb_plan_set_external_eps(fdb_plan *plan, const double *d_eps);
+
+/* ---- Multi-GPU behind the C ABI — no NCCL on the data path ---------------------------------------------
+ * Colours (dense plans: column blocks) are independent given x: every GPU evaluates its share and its diff+scatter
+ * kernel stores the entries it owns straight into ONE Jacobian buffer (the root's) through peer-mapped memory over
+ * NVLink — the final gather is the kernel's own store.
+ *
+ * (1) ONE process, n devices — what a Julia host needs to reach several GPUs from a single
+ *     finite_difference_jacobian!(J, f, x, cache) call (jacobians.jl:504-514): fdb_group_create_* builds one plan per
+ *     device (rank i of n; devices[0] is the root and owns x, J, fx), enables peer access to the root, and
+ *     fdb_group_jacobian pushes x to the members, runs every member's colour loop on its own stream and joins them on
+ *     the caller's stream with CUDA events (asynchronous; no host synchronisation).  ctx[i] is the callback context of
+ *     member i (f! is invoked with device-i pointers and stream).  Device ordinals may repeat (two members on one GPU).
+ *     Dense groups: member i fills its column block of the root's J.  Forward / central plans. */
+typedef struct fdb_group fdb_group;
+fdb_status fdb_group_create_csc(fdb_group **group, int n_devices, const int *devices, int64_t m, int64_t n,
+                                const int64_t *colptr, const int64_t *rowval, int jkind, const int64_t *j_colptr,
+                                const int64_t *j_rowval, int64_t ldJ, const int64_t *colorvec, const fdb_plan_opts *opts);
+fdb_status fdb_group_create_banded(fdb_group **group, int n_devices, const int *devices, int64_t m, int64_t n, int64_t l,
+                                   int64_t u, int jkind, int64_t ldJ, const int64_t *colorvec, const fdb_plan_opts *opts);
+fdb_status fdb_group_create_dense(fdb_group **group, int n_devices, const int *devices, int64_t m, int64_t n, int64_t ldJ,
+                                  const fdb_plan_opts *opts);
+fdb_status fdb_group_destroy(fdb_group *group);
+fdb_status fdb_group_size(const fdb_group *group, int *n_members);
+/* member i's plan (owned by the group): fdb_plan_info / fdb_plan_counters / fdb_plan_get_eps / fdb_plan_color_owner */
+fdb_status fdb_group_plan(const fdb_group *group, int member, fdb_plan **plan);
+/* arguments as fdb_jacobian; d_x, d_J, d_fx, d_f_in live on devices[0], `stream` is a stream of devices[0] */
+fdb_status fdb_group_jacobian(fdb_group *group, fdb_fn f, void *const *ctx, const double *d_x, double *d_J, double *d_fx,
+                              const double *d_f_in, double relstep, double absstep, double dir, void *stream);
+
+/* (2) one process per GPU (torchrun / MPI style): create the plan with opts.rank / opts.world and opts.shared_j = 1, map
+ *     the root's J with fdb_ipc_open and pass THAT pointer as d_J (or keep a private J and name the root's buffer with
+ *     fdb_plan_set_peers).  fdb_sync is the device-side barrier that orders the ranks: a flag block per rank in peer
+ *     memory, fdb_sync_barrier enqueues one tiny kernel that signals every peer (st.release.sys) and waits for every
+ *     peer's signal (ld.acquire.sys) — stream-ordered, no host involvement, replayable inside a CUDA graph.
+ *     Typical call:  barrier (root finished reading J, and zero-filled it if needed)  ->  fdb_jacobian  ->  barrier.
+ *       fdb_sync_flags      this rank's flag block (a dedicated allocation: export it with fdb_ipc_get_handle)
+ *       fdb_sync_set_peers  every rank's flag block as mapped on this device (fdb_ipc_open), indexed by rank */
+typedef struct fdb_sync fdb_sync;
+fdb_status fdb_sync_create(fdb_sync **sync, int rank, int world, int device /* -1: current */);
+fdb_status fdb_sync_flags(fdb_sync *sync, void **d_flags);
+fdb_status fdb_sync_set_peers(fdb_sync *sync, void *const *d_flags_by_rank);
+fdb_status fdb_sync_barrier(fdb_sync *sync, void *stream);
+fdb_status fdb_sync_destroy(fdb_sync *sync);
 
 /* ---- Jacobian-vector product: finite_difference_jvp!(jvp, f, x, v, cache::JVPCache, f_in; relstep, absstep, dir)
  *      src/jvp.jl:238-274 — eps from sqrt(abs(dot(x, v))) (computed on the device), forward: f(fx1,x), f(jvp,x+eps v);

@@ -146,8 +146,9 @@ int fdo_finite_difference_jacobian(const fdo_problem *P, double *J, fdo_fn f, vo
   const int nt = o->nthreads > 1 ? o->nthreads : 1;
   const int fdtype = o->fdtype;
   if (fdtype != FDO_FORWARD && fdtype != FDO_CENTRAL) return 2; /* fdtype_error, epsilons.jl:159-167 */
-  double relstep = o->relstep > 0 ? o->relstep : fdo_default_relstep(fdtype); /* :508 */
-  double absstep = o->absstep > 0 ? o->absstep : relstep;                     /* :509 */
+  /* NaN = keyword not given; any other value (0 included) is used as passed, like the reference's keywords */
+  double relstep = isnan(o->relstep) ? fdo_default_relstep(fdtype) : o->relstep; /* :508 */
+  double absstep = isnan(o->absstep) ? relstep : o->absstep;                     /* :509 */
   double dir = o->dir;
   double *x1 = cache->x1, *x2 = cache->x2, *fx = cache->fx, *fx1 = cache->fx1; /* :518 */
   o->fcalls = 0;
@@ -351,8 +352,8 @@ int fdo_finite_difference_jvp(double *jvp, fdo_fn f, void *ctx, const double *x,
                               double dir, const double *eps_override, double *eps_out, int64_t *fcalls) {
   if (!jvp || !f || !x || !v || !x1 || !fx1) return 1;
   if (fdtype != FDO_FORWARD && fdtype != FDO_CENTRAL) return 2;   /* :248-250 complex rejected; fdtype_error :270 */
-  if (!(relstep > 0)) relstep = fdo_default_relstep(fdtype);      /* :245 */
-  if (!(absstep > 0)) absstep = relstep;                          /* :246 */
+  if (isnan(relstep)) relstep = fdo_default_relstep(fdtype);      /* :245 */
+  if (isnan(absstep)) absstep = relstep;                          /* :246 */
   double d = 0.0;
   for (int64_t j = 0; j < n; ++j) d += x[j] * v[j];
   const double tmp = sqrt(fabs(d));                               /* :252 */

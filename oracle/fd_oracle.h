@@ -89,8 +89,8 @@ typedef struct {
 
 typedef struct {
   int fdtype;            /* FDO_FORWARD / FDO_CENTRAL */
-  double relstep;        /* <=0 -> default_relstep(fdtype, Float64) */
-  double absstep;        /* <=0 -> relstep  (jacobians.jl:510) */
+  double relstep;        /* NaN -> default_relstep(fdtype, Float64); any other value as passed */
+  double absstep;        /* NaN -> relstep  (jacobians.jl:510); any other value (0 included) as passed */
   double dir;            /* forward only; 1.0 default (`dir=true`) */
   const int64_t *colorvec; /* n entries, 1-based colours; NULL -> 1:n */
   const double *f_in;    /* forward: precomputed f(x) or NULL */

@@ -206,7 +206,7 @@ def as_fn(f):
     return FDO_FN(tramp), state
 
 
-def jacobian(P: Problem, J: np.ndarray, f, x: np.ndarray, *, fdtype=FORWARD, relstep=0.0, absstep=0.0, dir=1.0,
+def jacobian(P: Problem, J: np.ndarray, f, x: np.ndarray, *, fdtype=FORWARD, relstep=None, absstep=None, dir=1.0,
              colorvec=None, f_in=None, eps_override=None, no_drift=False, nthreads=1, cache=None, cacheless=False,
              ctx=None):
     """Run the oracle's cached (default) or cache-less finite_difference_jacobian!.
@@ -223,6 +223,8 @@ def jacobian(P: Problem, J: np.ndarray, f, x: np.ndarray, *, fdtype=FORWARD, rel
     eps_out = np.zeros(max(maxcolor, 1), np.float64)
     eo = None if eps_override is None else np.ascontiguousarray(eps_override, dtype=np.float64)
     fin = None if f_in is None else np.ascontiguousarray(f_in, dtype=np.float64)
+    relstep = float("nan") if relstep is None else float(relstep)     # NaN = keyword not given
+    absstep = float("nan") if absstep is None else float(absstep)
     opts = _Opts(fdtype, relstep, absstep, float(dir), _pi64(cv), _p64(fin), _p64(eo), _p64(eps_out),
                  int(bool(no_drift)), int(nthreads), 0)
     if ctx is None:
@@ -278,7 +280,7 @@ def jacobian_complex(P: Problem, J: np.ndarray, f, x: np.ndarray, *, colorvec=No
     return {"fcalls": int(calls.value)}
 
 
-def jvp(f, x: np.ndarray, v: np.ndarray, m: int, *, fdtype=FORWARD, relstep=0.0, absstep=0.0, dir=1.0, f_in=None,
+def jvp(f, x: np.ndarray, v: np.ndarray, m: int, *, fdtype=FORWARD, relstep=None, absstep=None, dir=1.0, f_in=None,
         eps_override=None, ctx=None):
     """finite_difference_jvp!(jvp, f, x, v, cache, f_in) (src/jvp.jl:238-274).  Returns dict(jvp, eps, fcalls, x1, fx1)."""
     L = lib()
@@ -301,6 +303,8 @@ def jvp(f, x: np.ndarray, v: np.ndarray, m: int, *, fdtype=FORWARD, relstep=0.0,
     eo = None if eps_override is None else np.array([eps_override], dtype=np.float64)
     eps_out = np.zeros(1)
     calls = C.c_int64(0)
+    relstep = float("nan") if relstep is None else float(relstep)
+    absstep = float("nan") if absstep is None else float(absstep)
     rc = fn(_p64(out), fptr, cptr, _p64(np.ascontiguousarray(x)), _p64(np.ascontiguousarray(v)), m, n, _p64(x1), _p64(fx1),
             _p64(fin), fdtype, relstep, absstep, float(dir), _p64(eo), _p64(eps_out), C.byref(calls))
     if rc != 0:

@@ -44,7 +44,7 @@ def test_header_symbols_exported_and_bound(pkg):
     assert not missing, f"declared in include/fdjac_b200.h but not exported: {missing}"
     assert sorted(L.ABI_SYMBOLS) == declared, "ctypes table and header disagree"
     lib = L.lib()                      # binds every symbol; AttributeError if one is absent
-    assert lib.fdb_abi_version() == 1
+    assert lib.fdb_abi_version() == 2
 
 
 def test_synth_header_symbols(pkg):

@@ -706,7 +706,7 @@ def test_host_buffer_entry_point(pkg, oracle, dev):
     ctx = pkg._lib.TridiagCtx(N, 0)
     L = pkg._lib
     L.check(L.lib().fdb_jacobian_host(plan.handle, C.cast(L.synth().fdbs_tridiag, C.c_void_p), C.cast(C.pointer(ctx), C.c_void_p),
-                                      xh.ctypes.data, Jh.ctypes.data, fxh.ctypes.data, None, 0.0, 0.0, 1.0))
+                                      xh.ctypes.data, Jh.ctypes.data, fxh.ctypes.data, None, float("nan"), float("nan"), 1.0))
     ref = np.full(len(rowval), np.nan)
     r = oracle.jacobian(oracle.Problem.csc_same(N, N, colptr, rowval), ref, oracle.native_fn("synth_tridiag"), np.array(xh),
                         colorvec=cv, eps_override=plan.eps(), ctx=oracle.SynthTridiagCtx(N, 1))
