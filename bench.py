@@ -549,7 +549,7 @@ def measure(pkg, step, plan, steps, warmup, barrier, dist_max=None, spin_s=0.0):
     return dict(ms_total=ms_total, ms_step=ms_total / steps, c0=c0, c1=c1, scat_ms=scat_ms, scat_n=scat_n, tsteps=tsteps)
 
 
-def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0):
+def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0, sample_clocks=False):
     """One workload on one GPU: build, measure, parity record.  Returns (record, prob, plan, nnz)."""
     import torch
     prob = build_gpu_problem(pkg, workload, fdtype, dev, 0, 1, args.max_batch, args.graph, strategy=strategy)
@@ -567,7 +567,11 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0):
     barrier()
     first_call_ms = (time.perf_counter() - t_first) * 1e3
     plan = cache._last_plan
+    # nvidia-smi samples every 100 ms: the sampler runs over warm-up (>= spin_s of the same step), the timed region and the
+    # kernel-timing pass — all the same kernel sequence under load — and not over problem construction
+    clocks = Clocks(dev.index if dev.index is not None else 0) if sample_clocks else None
     m = measure(pkg, step, plan, steps, args.warmup, barrier, spin_s=spin_s)
+    clk = clocks.stop() if clocks else None
     info = plan.info()
     nnz = prob["nnz"] if prob["nnz"] is not None else info["n_entries"]
     f_points = m["c1"]["f_points"] - m["c0"]["f_points"]
@@ -583,7 +587,7 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0):
         "gpu_launches": int(lib_launches + f_inv * f_launch_per_point),
         "gpu_launches_detail": {"library_kernels": int(lib_launches), "f_callback_invocations": int(f_inv)},
         "scatter_strategy": {0: "fused storage-order pass", 1: "colour-major lists per group"}[info["strategy"]] if info["sp_kind"] == 1 else None,
-        "scatter_groups": info["n_groups"],
+        "scatter_groups": info["n_groups"], "clocks": clk,
     }
     return rec, prob, plan, nnz
 
@@ -606,9 +610,9 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
         return gpu_arm_multi(args, pkg, dev, rank, world)
     workload, fdtype = args.workload, args.fdtype
-    clocks = Clocks(local_rank)
-    rec, prob, plan, nnz = run_single(pkg, workload, fdtype, dev, args, args.steps, spin_s=0.6, strategy=args.strategy)
-    clk = clocks.stop()
+    rec, prob, plan, nnz = run_single(pkg, workload, fdtype, dev, args, args.steps, spin_s=0.6, strategy=args.strategy,
+                                      sample_clocks=True)
+    clk = rec.pop("clocks")
     J, f, x = prob["J"], prob["f"], prob["x"]
     info = plan.info()
 
@@ -723,7 +727,6 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
     if workload not in ("c4", "c5"):
         raise SystemExit("--gpus N>1 runs c4 (colour shards), c5 (column blocks) or c2 with --shard columns")
 
-    clocks = Clocks(dev.index) if rank == 0 else None
     strong = None
     J1 = eps1 = None
     if workload == "c4":
@@ -758,7 +761,9 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
     barrier()
     first_call_ms = (time.perf_counter() - t_first) * 1e3
     plan = cache._last_plan
+    clocks = Clocks(dev.index) if rank == 0 else None
     m = measure(pkg, step, plan, args.steps, args.warmup, barrier, dist_max=dist_max, spin_s=0.6)
+    clk = clocks.stop() if clocks else None
     info = plan.info()
     nnz = prob["nnz"]
     ms_step = m["ms_step"]
@@ -823,7 +828,6 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
         med, reps = time_cpu(run, budget_s=10.0, max_reps=3)
         cpu = {"value": cnnz / med, "unit": "nnz/s", "cores": 1, "kind": "port",
                "sample": f"{reps} full Jacobian(s) of {desc} (median {med:.3f} s; problem scaled by 0.2)", "f_evals_per_s": cf / med}
-    clk = clocks.stop() if clocks else None
     if rank == 0:
         line = {
             "metric": "jacobian_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps,

@@ -14,8 +14,8 @@ The directory name contains a dot, so it is imported through /root/repo/_bootstr
 from . import _lib  # noqa: F401
 from .api import (BandedBlockBandedMatrix, BandedMatrix, BlockBandedMatrix, DenseColumnBlock, JacobianCache, JVPCache, NativeFn, Plan, SparseMatrixCSC, Tridiagonal, compute_epsilon,
                   default_relstep, finite_difference_jacobian_, finite_difference_jacobian_b, finite_difference_jvp_,
-                  make_plan, pinned_empty, resize_, zeros_colmajor)
+                  check_coloring, make_plan, matrix_colors, pinned_empty, resize_, zeros_colmajor)
 
 __all__ = ["BandedBlockBandedMatrix", "BandedMatrix", "BlockBandedMatrix", "DenseColumnBlock", "JacobianCache", "JVPCache", "finite_difference_jvp_", "NativeFn", "Plan", "SparseMatrixCSC", "Tridiagonal", "compute_epsilon",
-           "default_relstep", "finite_difference_jacobian_", "finite_difference_jacobian_b", "make_plan",
+           "default_relstep", "finite_difference_jacobian_", "finite_difference_jacobian_b", "make_plan", "matrix_colors", "check_coloring",
            "pinned_empty", "resize_", "zeros_colmajor"]

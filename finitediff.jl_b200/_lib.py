@@ -95,6 +95,9 @@ ABI_SYMBOLS = {
     "fdb_sync_set_peers": (_int, [_vp, C.POINTER(_vp)]),
     "fdb_sync_barrier": (_int, [_vp, _vp]),
     "fdb_sync_destroy": (_int, [_vp]),
+    "fdb_matrix_colors_banded": (_int, [_i64, _i64, _i64, _vp, _vp]),
+    "fdb_matrix_colors_csc": (_int, [_i64, _i64, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "fdb_check_coloring_csc": (_int, [_i64, _i64, _vp, _vp, _vp, C.POINTER(_i64)]),
     "fdb_jvp_plan_create": (_int, [_PP, _i64, _i64, C.POINTER(PlanOpts)]),
     "fdb_jvp": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp]),
     "fdb_host_alloc": (_int, [_PP, C.c_size_t]),

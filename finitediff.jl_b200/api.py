@@ -708,6 +708,57 @@ def resize_(cache: JacobianCache, i: int):
     return None
 
 
+# ------------------------------------------------------------------------------------------------ colouring
+def matrix_colors(A, device=None) -> torch.Tensor:
+    """ArrayInterface.matrix_colors(A) on the device: an Int64 CUDA tensor of 1-based colours, ready to be passed as
+    `colorvec`.  Tridiagonal -> 1,2,3,...; BandedMatrix(l,u) -> cycle 1:(l+u+1) (ArrayInterface's closed forms);
+    SparseMatrixCSC -> a valid distance-2 column colouring (deterministic Jones-Plassmann, fdb_matrix_colors_csc);
+    dense tensors -> 1:n (ArrayInterface: eachindex of the columns)."""
+    lib = L.lib()
+    if isinstance(A, Tridiagonal):
+        n, l, u = A.n, 1, 1
+        dev = A.buf.device if device is None else torch.device(device)
+    elif isinstance(A, BandedMatrix):
+        n, l, u = A.n, A.l, A.u
+        dev = (A.data.device if isinstance(A.data, torch.Tensor) and A.data.is_cuda else torch.device("cuda")) if device is None else torch.device(device)
+    elif isinstance(A, SparseMatrixCSC):
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        out = torch.zeros(max(A.n, 1), dtype=torch.int64, device=dev)
+        cp, k1 = _index_ptr(A.colptr)
+        rv, k2 = _index_ptr(A.rowval)
+        nc, nr = C.c_int64(), C.c_int64()
+        with torch.cuda.device(dev):
+            L.check(lib.fdb_matrix_colors_csc(A.m, A.n, cp, rv, out.data_ptr(), C.byref(nc), C.byref(nr)))
+        out = out[: A.n]
+        out.n_colors, out.n_rounds = nc.value, nr.value
+        return out
+    elif isinstance(A, BandedBlockBandedMatrix):
+        return torch.from_numpy(A.matrix_colors()).to(torch.device("cuda") if device is None else torch.device(device))
+    elif isinstance(A, torch.Tensor):
+        n = A.shape[1] if A.dim() == 2 else 1
+        return torch.arange(1, n + 1, dtype=torch.int64, device=A.device if A.is_cuda else (device or "cuda"))
+    else:
+        raise TypeError(f"matrix_colors: unsupported type {type(A)}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.fdb_matrix_colors_banded(n, l, u, out.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out[:n]
+
+
+def check_coloring(A: "SparseMatrixCSC", colorvec) -> int:
+    """Number of (row, colour) collisions of `colorvec` on the CSC pattern (0 = valid for the decompression)."""
+    cp, k1 = _index_ptr(A.colptr)
+    rv, k2 = _index_ptr(A.rowval)
+    cv, k3 = _index_ptr(colorvec)
+    out = C.c_int64()
+    L.check(L.lib().fdb_check_coloring_csc(A.m, A.n, cp, rv, cv, C.byref(out)))
+    return out.value
+
+
 # ------------------------------------------------------------------------------------------------ the public call
 def _as_fn(f, m, n, device, plan_batch, complex_=False):
     if isinstance(f, NativeFn):

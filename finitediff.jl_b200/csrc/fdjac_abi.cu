@@ -17,6 +17,7 @@
 #include <type_traits>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -24,7 +25,9 @@
 #include "kernels_perturb.cuh"
 #include "kernels_plan.cuh"
 #include "kernels_scatter.cuh"
+#include "kernels_staged.cuh"
 #include "kernels_jvp.cuh"
+#include "kernels_color.cuh"
 
 using namespace fdb;
 
@@ -111,6 +114,11 @@ struct fdb_plan {
   int32_t eps_group = 1;   // largest aligned lane group without a repeated colour (color_lane_conflicts)
   const double *ext_eps = nullptr;   // step sizes supplied by the caller (fdb_plan_set_external_eps), device, >= C entries
   unsigned int *ticket = nullptr;   // last-block-done counter of color_sumsq_reg
+  // eps from the per-colour column lists (CSC plans with more than kEpsRegColors colours)
+  bool eps_lists = false;
+  int64_t *bucket_start_d = nullptr, *chunk_base_d = nullptr;
+  double *eps_list_partial = nullptr;
+  int64_t eps_list_max_chunks = 0;
   bool peers_aligned = true;
   bool shared_J = false;            // member of an fdb_group: J is shared with the other members (root zero-fills it)
   // scratch
@@ -131,6 +139,11 @@ struct fdb_plan {
   int64_t *cm_start = nullptr;        // device [n_local + 1]
   std::vector<int64_t> cm_start_h;    // host copy; [n_local] .. cm_invalid_end = entries of columns without a valid colour
   int64_t cm_invalid_end = 0;
+  // TMA-staged form of the fused pass (row-local patterns; kernels_staged.cuh)
+  uint16_t *row16 = nullptr;
+  int32_t *tile_w0 = nullptr;
+  int32_t stage_W = 0;
+  bool staged = false;
   std::vector<int64_t> bucket_start;   // [C+2] offsets into cols_by_color; bucket C = columns without a valid colour
   int lanes = 1;
   double mean_row_jump = 0.0;
@@ -387,6 +400,70 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   return FDB_OK;
 }
 
+// Per-colour column lists (cols_by_color, ascending inside a colour; P->bucket_start must be set) and, for more colours
+// than the register path takes, the chunk tables of the list-based eps pass.
+static fdb_status build_color_lists(fdb_plan *P) {
+  const int64_t n = P->n;
+  const int32_t C = P->C;
+  if (!P->cols_by_color) TRY(P->alloc_t(&P->cols_by_color, (size_t)std::max<int64_t>(n, 1)));
+  if (n > 0) {
+    // a stable radix sort of the column ids by colour (deterministic: the list-based eps pass sums in list order, and
+    // sharded and unsharded plans must produce the same bits)
+    uint32_t *k_in = nullptr, *k_out = nullptr;
+    int32_t *v_in = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    auto cleanup = [&]() { cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(d_tmp); };
+    cudaError_t e = cudaMalloc((void **)&k_in, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&k_out, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&v_in, (size_t)n * 4);
+    if (e == cudaSuccess) {
+      dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+        using CT = decltype(tag);
+        color_sort_keys<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, n, C, k_in, v_in);
+        return FDB_OK;
+      });
+      int end_bit = 1;
+      while (end_bit < 32 && ((uint64_t)1 << end_bit) <= (uint64_t)C) ++end_bit;
+      e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, P->cols_by_color, (int)n, 0, end_bit);
+      if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+      if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, k_in, k_out, v_in, P->cols_by_color, (int)n, 0, end_bit);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(FDB_ERR_CUDA, "column lists: %s", cudaGetErrorString(e));
+  }
+  // step sizes from the column lists (more colours than the register path takes)
+  if (C > kEpsRegColors && C <= (1 << 22) && n > 0) {
+    std::vector<int64_t> cb((size_t)C + 1, 0);
+    int64_t maxc = 1;
+    for (int32_t k = 0; k < C; ++k) {
+      const int64_t len = P->bucket_start[(size_t)k + 1] - P->bucket_start[(size_t)k];
+      const int64_t nc = (len + kEpsListChunk - 1) / kEpsListChunk;
+      cb[(size_t)k + 1] = cb[(size_t)k] + nc;
+      maxc = std::max(maxc, nc);
+    }
+    TRY(P->alloc_t(&P->bucket_start_d, (size_t)C + 2));
+    TRY(P->alloc_t(&P->chunk_base_d, (size_t)C + 1));
+    TRY(P->alloc_t(&P->eps_list_partial, (size_t)std::max<int64_t>(cb[(size_t)C], 1)));
+    CU(cudaMemcpy(P->bucket_start_d, P->bucket_start.data(), ((size_t)C + 2) * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(P->chunk_base_d, cb.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice));
+    P->eps_list_max_chunks = maxc;
+    P->eps_lists = true;
+  }
+  return FDB_OK;
+}
+
+// host offsets of the per-colour column buckets from their device counts ([C+1]: bucket C = columns without a valid colour)
+static fdb_status bucket_offsets(fdb_plan *P, const unsigned long long *d_bucket_counts) {
+  const int32_t C = P->C;
+  std::vector<unsigned long long> bc((size_t)C + 1, 0);
+  CU(cudaMemcpy(bc.data(), d_bucket_counts, ((size_t)C + 1) * 8, cudaMemcpyDeviceToHost));
+  P->bucket_start.assign((size_t)C + 2, 0);
+  for (int32_t k = 0; k <= C; ++k) P->bucket_start[(size_t)k + 1] = P->bucket_start[(size_t)k] + (int64_t)bc[(size_t)k];
+  return FDB_OK;
+}
+
 // gather kernel for build_cm_lists: block b copies the column bucket of local colour (or of the invalid bucket) b
 __global__ void __launch_bounds__(kThreads)
 cm_gather_cols(const int32_t *__restrict__ cols_by_color, const int64_t *__restrict__ src_start /* [nseg] */,
@@ -467,6 +544,33 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   if ((int64_t)last_off + last_cnt != e_local)
     return fail(FDB_ERR_INVALID, "internal: colour-major list holds %lld entries, expected %lld", (long long)last_off + last_cnt,
                 (long long)e_local);
+  return FDB_OK;
+}
+
+// TMA-staged fused pass: eligible when the whole Jacobian is one resident group on one rank, the destination is the
+// identity (CSC nzval) and every 1024-entry tile touches a short row window (row-local pattern).
+static fdb_status try_stage_plan(fdb_plan *P) {
+  P->staged = false;
+  const char *off = getenv("FDB_NO_STAGED");
+  if (off && off[0] == '1') return FDB_OK;
+  if (P->sp_kind != SP_CSC || P->dest != nullptr || P->strategy != 0 || P->world != 1 || P->n_groups != 1) return FDB_OK;
+  if (P->fdtype == FDB_COMPLEX || P->C < 1) return FDB_OK;
+  const int nwin = P->fdtype == FDB_CENTRAL ? 2 * P->C : P->C + 1;
+  const int64_t ntiles = P->E / kTile;
+  if (nwin > kStageMaxWin || ntiles < 1) return FDB_OK;
+  unsigned int *d_span = nullptr;
+  TRY(P->alloc_t(&d_span, 1));
+  CU(cudaMemset(d_span, 0, 4));
+  TRY(P->alloc_t(&P->tile_w0, (size_t)ntiles));
+  TRY(P->alloc_t(&P->row16, (size_t)ntiles * kTile));
+  stage_prepare<<<(int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16), kThreads>>>(P->row32, ntiles, P->tile_w0, P->row16, d_span);
+  unsigned int span = 0;
+  CU(cudaMemcpy(&span, d_span, 4, cudaMemcpyDeviceToHost));
+  const int64_t W = ((int64_t)span + 1) & ~(int64_t)1;
+  const size_t smem = (size_t)kStages * nwin * W * 8 + kStages * 8 + (size_t)P->C * 8;
+  if (span == 0 || span > 65535 || smem > (size_t)kStageMaxSmem) return FDB_OK;   // not row-local enough: keep the gather form
+  P->stage_W = (int32_t)W;
+  P->staged = true;
   return FDB_OK;
 }
 
@@ -681,14 +785,7 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     for (int32_t k = 0; k <= C; ++k) P->bucket_start[(size_t)k + 1] = P->bucket_start[(size_t)k] + (int64_t)bc[(size_t)k];
     std::vector<unsigned long long> cursor(P->bucket_start.begin(), P->bucket_start.begin() + C + 1);
     cudaMemcpy(d_bucket, cursor.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice);
-    if (n > 0) {
-      PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
-        using CT = decltype(tag);
-        bucket_columns<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, n, C, d_bucket, P->cols_by_color);
-        CU(cudaGetLastError());
-        return FDB_OK;
-      }));
-    }
+    PLAN_TRY(build_color_lists(P));
     if (nnz > 1) {
       row_jump_sum<<<P->grid(nnz), kThreads>>>(P->row32, nnz, d_jump);
       unsigned long long js = 0;
@@ -713,6 +810,7 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
   }
   PLAN_TRY(finish_colored_plan(P, opts, cnt));
   if (P->strategy == 1) PLAN_TRY(build_cm_lists(P, cnt));
+  PLAN_TRY(try_stage_plan(P));
   // B_alg = 32*nnz + 16*n + 8 (valid colouring; Int64 indices as at the ABI)
   P->alg_bytes = 32 * nnz + 16 * n + 8;
   {
@@ -934,6 +1032,8 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
         const int64_t C = std::max<int32_t>(P->C, 1);
         const int64_t owned = P->world > 1 ? P->E * (int64_t)P->local_colors.size() / C : P->E;   // approx. share
         info->moved_bytes_scatter = P->E * (4 + ct) * std::max<int64_t>(P->n_groups, 1) + owned * (8 * slabs_read + 8 + (P->dest ? 8 : 0)) + fx_once;
+        if (P->staged)   // 16-bit row offsets; every slab row and f(x) row staged once
+          info->moved_bytes_scatter = P->E * (2 + ct + 8) + 8 * P->m * (int64_t)(P->fdtype == FDB_CENTRAL ? 2 * P->C : P->C + 1);
       }
     } else {
       info->moved_bytes_scatter = P->alg_bytes;
@@ -1085,6 +1185,18 @@ static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double a
     return FDB_OK;
   }
   EpsParams prm{P->fdtype == FDB_CENTRAL ? 1 : 0, relstep, absstep, dir};
+  if (P->eps_lists) {
+    const char *off = getenv("FDB_NO_EPS_LISTS");
+    if (!(off && off[0] == '1')) {
+      dim3 grid((unsigned)std::min<int64_t>(P->eps_list_max_chunks, 1024), (unsigned)std::min<int32_t>(C, 65535));
+      color_sumsq_lists<<<grid, kThreads, 0, s>>>(x, P->cols_by_color, P->bucket_start_d, P->chunk_base_d, C, P->eps_list_partial);
+      finalize_eps_lists<<<(int)std::min<int64_t>(((int64_t)C * 32 + kThreads - 1) / kThreads, (int64_t)P->sm_count * 8), kThreads, 0, s>>>(
+          P->eps_list_partial, P->chunk_base_d, C, prm, P->eps, P->sumsq);
+      P->cnt.kernel_launches += 2;
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }
+  }
   if (C <= kEpsRegColors) {
     const int64_t ntiles = (P->n + kTile - 1) / kTile;
     const int aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
@@ -1283,7 +1395,22 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
         const int64_t tiles = (P->E + kTile - 1) / kTile;
         // single group on a single rank: every valid colour is resident -> the FULL variant (no ownership tests)
         const bool full = P->n_groups == 1 && P->world == 1 && P->n_peers == 0;
-        if (full) {
+        // staged form: needs 16-byte aligned sources and (forward) ldF readable doubles behind f(x)
+        bool staged = full && P->staged && MODE != kComplex;
+        if (staged && MODE == kForward)
+          staged = (reinterpret_cast<uintptr_t>(vfx) & 15) == 0 && ((P->m & 1) == 0 || vfx == P->fx_own);
+        if (staged) {
+          if constexpr (MODE != kComplex) {
+            StagedArgs sa{};
+            sa.row16 = P->row16; sa.ecolor = P->ecolor; sa.tile_w0 = P->tile_w0; sa.row32 = P->row32;
+            sa.fx = vfx; sa.Fp = P->Fp; sa.Fm = P->Fm; sa.eps = P->eps; sa.J = J; sa.C = P->C; sa.W = P->stage_W;
+            sa.ldF = sF; sa.src_len = P->ldF; sa.E = P->E; sa.j_aligned = a.j_aligned;
+            const int nwin = CENTRAL ? 2 * P->C : P->C + 1;
+            const size_t ssm = (size_t)kStages * nwin * P->stage_W * 8 + kStages * 8 + (size_t)P->C * 8;
+            const int grid = resident_grid(P, diff_scatter_staged<CT, MODE>, ssm, tiles);
+            diff_scatter_staged<CT, MODE><<<grid, kThreads, ssm, s>>>(sa);
+          }
+        } else if (full) {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);
           diff_scatter_ident<CT, MODE, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
         } else {
@@ -1494,6 +1621,21 @@ fdb_status fdb_eps_plan_create(fdb_plan **plan, int64_t n, const int64_t *colorv
   I64View cv;
   PLAN_TRY(setup_colors(P, colorvec, cv));
   PLAN_TRY(alloc_eps_buffers(P));
+  // the same list-based eps pass as the Jacobian plans: a column block's external step sizes are then bit-identical to
+  // the ones the unsharded plan computes for itself
+  if (P->C > kEpsRegColors && n > 0) {
+    unsigned long long *d_bucket = nullptr;
+    PLAN_TRY(P->alloc_t(&d_bucket, (size_t)P->C + 2));
+    cudaMemset(d_bucket, 0, ((size_t)P->C + 2) * 8);
+    PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      count_color_buckets<CT><<<P->grid(n), kThreads>>>((const CT *)P->jcolor, n, P->C, d_bucket);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+    PLAN_TRY(bucket_offsets(P, d_bucket));
+    PLAN_TRY(build_color_lists(P));
+  }
   return FDB_OK;
 }
 

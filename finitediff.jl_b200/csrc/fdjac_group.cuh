@@ -294,3 +294,134 @@ fdb_status fdb_sync_destroy(fdb_sync *s) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ on-device colouring
+// ArrayInterface.matrix_colors analogues (kernels_color.cuh).  Plan-time operations: they synchronise.
+struct CsrPattern {
+  int32_t *rowptr = nullptr, *rcols = nullptr;
+  I64View cp, rv;
+  int64_t nnz = 0;
+  ~CsrPattern() { cudaFree(rowptr); cudaFree(rcols); }
+};
+
+static fdb_status build_csr_pattern(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, CsrPattern &P) {
+  if (m < 0 || n < 0 || m > 0x7FFFFFF0LL || n > 0x7FFFFFF0LL) return fail(FDB_ERR_INVALID, "m, n must be in [0, 2^31)");
+  if (!colptr) return fail(FDB_ERR_INVALID, "colptr is NULL");
+  TRY(view_i64(colptr, n + 1, P.cp));
+  int64_t last = 1;
+  CU(cudaMemcpy(&last, P.cp.d + n, 8, cudaMemcpyDeviceToHost));
+  P.nnz = last - 1;
+  if (P.nnz < 0 || P.nnz > 0x7FFFFFF0LL) return fail(FDB_ERR_INVALID, "nnz=%lld unsupported", (long long)P.nnz);
+  if (P.nnz > 0 && !rowval) return fail(FDB_ERR_INVALID, "rowval is NULL");
+  TRY(view_i64(rowval, P.nnz, P.rv));
+  uint32_t *d_err = nullptr;
+  int32_t *cnt = nullptr, *cursor = nullptr;
+  void *d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto cleanup = [&]() { cudaFree(d_err); cudaFree(cnt); cudaFree(cursor); cudaFree(d_tmp); };
+#define CSR_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
+    return fail(FDB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  CSR_CU(cudaMalloc((void **)&d_err, 4));
+  CSR_CU(cudaMemset(d_err, 0, 4));
+  CSR_CU(cudaMalloc((void **)&cnt, ((size_t)m + 1) * 4));
+  CSR_CU(cudaMemset(cnt, 0, ((size_t)m + 1) * 4));
+  CSR_CU(cudaMalloc((void **)&cursor, ((size_t)m + 1) * 4));
+  CSR_CU(cudaMemset(cursor, 0, ((size_t)m + 1) * 4));
+  CSR_CU(cudaMalloc((void **)&P.rowptr, ((size_t)m + 1) * 4));
+  CSR_CU(cudaMalloc((void **)&P.rcols, (size_t)std::max<int64_t>(P.nnz, 1) * 4));
+  const int gb = (int)std::max<int64_t>(1, std::min<int64_t>((std::max<int64_t>(P.nnz, n + 1) + kThreads - 1) / kThreads, 148 * 16));
+  validate_colptr<<<gb, kThreads>>>(P.cp.d, n, P.nnz, d_err);
+  if (P.nnz > 0) csr_count_rows<<<gb, kThreads>>>(P.rv.d, P.nnz, m, cnt, d_err);
+  uint32_t herr = 0;
+  CSR_CU(cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost));
+  if (herr) { cleanup(); return fail(FDB_ERR_INVALID, "invalid CSC pattern (%s)", (herr & 1u) ? "colptr" : "row index outside 1..m"); }
+  CSR_CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, P.rowptr, (int)(m + 1)));
+  CSR_CU(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+  CSR_CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, cnt, P.rowptr, (int)(m + 1)));
+  if (n > 0 && P.nnz > 0) csr_fill<<<gb, kThreads>>>(P.cp.d, P.rv.d, n, m, P.rowptr, cursor, P.rcols);
+  CSR_CU(cudaDeviceSynchronize());
+#undef CSR_CU
+  cleanup();
+  return FDB_OK;
+}
+
+extern "C" {
+
+fdb_status fdb_matrix_colors_banded(int64_t n, int64_t l, int64_t u, int64_t *d_colorvec, void *stream) {
+  if (n < 0 || l + u + 1 < 1) return fail(FDB_ERR_INVALID, "invalid n / bandwidths");
+  if (n > 0 && !d_colorvec) return fail(FDB_ERR_INVALID, "colorvec is NULL");
+  if (n == 0) return FDB_OK;
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, 148 * 8));
+  cyclic_colors<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(n, l + u + 1, d_colorvec);
+  CU(cudaGetLastError());
+  return FDB_OK;
+}
+
+fdb_status fdb_matrix_colors_csc(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, int64_t *d_colorvec,
+                                 int64_t *n_colors, int64_t *n_rounds) {
+  if (n > 0 && !d_colorvec) return fail(FDB_ERR_INVALID, "colorvec is NULL");
+  int dev = 0;
+  TRY(check_device(nullptr, &dev));
+  if (n_colors) *n_colors = 0;
+  if (n_rounds) *n_rounds = 0;
+  if (n == 0) return FDB_OK;
+  CsrPattern P;
+  TRY(build_csr_pattern(m, n, colptr, rowval, P));
+  int32_t *col_a = nullptr, *col_b = nullptr;
+  unsigned long long *d_pending = nullptr;
+  int *d_max = nullptr;
+  auto cleanup = [&]() { cudaFree(col_a); cudaFree(col_b); cudaFree(d_pending); cudaFree(d_max); };
+#define COL_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); \
+    return fail(FDB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); } } while (0)
+  COL_CU(cudaMalloc((void **)&col_a, (size_t)n * 4));
+  COL_CU(cudaMalloc((void **)&col_b, (size_t)n * 4));
+  COL_CU(cudaMalloc((void **)&d_pending, 8));
+  COL_CU(cudaMalloc((void **)&d_max, 4));
+  COL_CU(cudaMemset(col_a, 0, (size_t)n * 4));
+  COL_CU(cudaMemset(d_max, 0, 4));
+  const int gb = (int)std::max<int64_t>(1, std::min<int64_t>((n + kThreads - 1) / kThreads, 148 * 16));
+  int64_t rounds = 0;
+  unsigned long long pending = (unsigned long long)n;
+  while (pending > 0) {
+    COL_CU(cudaMemset(d_pending, 0, 8));
+    jp_color_round<<<gb, kThreads>>>(P.cp.d, P.rv.d, P.rowptr, P.rcols, n, m, col_a, col_b, d_pending);
+    COL_CU(cudaMemcpy(&pending, d_pending, 8, cudaMemcpyDeviceToHost));
+    std::swap(col_a, col_b);
+    if (++rounds > 100000) { cleanup(); return fail(FDB_ERR_INVALID, "colouring did not converge"); }
+  }
+  colors_to_i64<<<gb, kThreads>>>(col_a, n, d_colorvec, d_max);
+  int mx = 0;
+  COL_CU(cudaMemcpy(&mx, d_max, 4, cudaMemcpyDeviceToHost));
+#undef COL_CU
+  cleanup();
+  if (n_colors) *n_colors = mx;
+  if (n_rounds) *n_rounds = rounds;
+  return FDB_OK;
+}
+
+fdb_status fdb_check_coloring_csc(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, const int64_t *colorvec,
+                                  int64_t *n_conflicts) {
+  if (!n_conflicts) return fail(FDB_ERR_INVALID, "NULL argument");
+  *n_conflicts = 0;
+  int dev = 0;
+  TRY(check_device(nullptr, &dev));
+  if (n == 0 || m == 0) return FDB_OK;
+  if (!colorvec) return FDB_OK;                     // 1:n: every column its own colour
+  CsrPattern P;
+  TRY(build_csr_pattern(m, n, colptr, rowval, P));
+  I64View cv;
+  TRY(view_i64(colorvec, n, cv));
+  unsigned long long *d_c = nullptr;
+  CU(cudaMalloc((void **)&d_c, 8));
+  cudaMemset(d_c, 0, 8);
+  const int gb = (int)std::max<int64_t>(1, std::min<int64_t>((m + kThreads - 1) / kThreads, 148 * 16));
+  count_color_conflicts<<<gb, kThreads>>>(P.rowptr, P.rcols, m, cv.d, d_c);
+  unsigned long long h = 0;
+  const cudaError_t e = cudaMemcpy(&h, d_c, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_c);
+  if (e != cudaSuccess) return fail(FDB_ERR_CUDA, "conflict count: %s", cudaGetErrorString(e));
+  *n_conflicts = (int64_t)h;
+  return FDB_OK;
+}
+
+}  // extern "C"

@@ -196,6 +196,69 @@ color_sumsq_win(const double *__restrict__ x, const CT *__restrict__ jcolor, int
   }
 }
 
+// ---- many colours, CSC plans: sums of squares from the per-colour column lists ----
+// The plan holds every colour's columns as one sorted list (cols_by_color, ascending inside a colour).  Colour k's sum is
+// computed from ITS list alone: chunks of kEpsListChunk columns, one block per chunk (fixed lane -> element mapping, fixed
+// reduction tree), then one warp per colour adds the chunk partials in order.  The value of eps_k therefore depends only
+// on (x, the colour's column set) — not on the number of GPUs, the launch geometry or the other colours — and the pass
+// reads 4 + 8 bytes per column instead of streaming x once per 512-colour window with shared-memory read-modify-writes
+// (r1: color_sumsq_win 70 us for C4's 64 colours = 0.64 TB/s; it stays for plans without column lists).
+constexpr int kEpsListChunk = 4096;
+
+__global__ void __launch_bounds__(kThreads)
+color_sumsq_lists(const double *__restrict__ x, const int32_t *__restrict__ cols_by_color,
+                  const int64_t *__restrict__ bucket_start /* [C+1] */, const int64_t *__restrict__ chunk_base /* [C+1] */,
+                  int32_t C, double *__restrict__ partial) {
+  __shared__ double s[kEpsWarps];
+  for (int32_t k = blockIdx.y; k < C; k += gridDim.y) {
+    const int64_t b0 = bucket_start[k], len = bucket_start[k + 1] - b0;
+    const int64_t nchunks = (len + kEpsListChunk - 1) / kEpsListChunk;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      const int64_t c0 = b0 + ch * kEpsListChunk;
+      int64_t c1 = c0 + kEpsListChunk;
+      if (c1 > b0 + len) c1 = b0 + len;
+      double v[kEpsListChunk / kThreads];
+#pragma unroll
+      for (int u = 0; u < kEpsListChunk / kThreads; ++u) {          // all gathers of the chunk in flight together
+        const int64_t i = c0 + u * kThreads + threadIdx.x;
+        v[u] = i < c1 ? __ldg(x + __ldcs(cols_by_color + i)) : 0.0;
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < kEpsListChunk / kThreads; ++u) acc += v[u] * v[u];
+      acc = warp_sum(acc);
+      if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kEpsWarps; ++w) t += s[w];
+        partial[chunk_base[k] + ch] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// one warp per colour: chunk partials in fixed order, then the step-size formula
+__global__ void __launch_bounds__(kThreads)
+finalize_eps_lists(const double *__restrict__ partial, const int64_t *__restrict__ chunk_base, int32_t C, EpsParams prm,
+                   double *__restrict__ eps, double *__restrict__ sumsq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * kThreads) >> 5;
+  for (int64_t k = warp; k < C; k += nwarps) {
+    const int64_t p0 = chunk_base[k], p1 = chunk_base[k + 1];
+    double t = 0.0;
+    for (int64_t p = p0 + lane; p < p1; p += 32) t += partial[p];
+    t = warp_sum(t);
+    if (lane == 0) {
+      eps[k] = eps_from_sumsq(t, prm);
+      if (sumsq) sumsq[k] = t;
+    }
+  }
+}
+
 // One warp per colour: fixed-order reduction over the block partials, then the step-size formula.
 __global__ void __launch_bounds__(kThreads)
 finalize_eps(const double *__restrict__ partial, int32_t nblocks, int32_t stride /* colours per partial row */,

@@ -228,6 +228,33 @@ colptr32_and_count(const int64_t *__restrict__ colptr, int64_t n, const CT *__re
   }
 }
 
+// column counts per colour bucket (bucket C = columns without a valid colour) — plans without a CSC colptr
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+count_color_buckets(const CT *__restrict__ jcolor, int64_t n, int32_t C, unsigned long long *__restrict__ bucket_count /* [C+1] */) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = blockIdx.x * (int64_t)kThreads + threadIdx.x; c < n; c += stride) {
+    uint32_t k = (uint32_t)jcolor[c];
+    if (k >= (uint32_t)C) k = (uint32_t)C;
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, k);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(bucket_count + k, (unsigned long long)__popc(peers));
+  }
+}
+
+// sort keys of the per-colour column lists: colour id, C for columns without a valid colour; values = the column ids
+template <typename CT>
+__global__ void __launch_bounds__(kThreads)
+color_sort_keys(const CT *__restrict__ jcolor, int64_t n, int32_t C, uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = blockIdx.x * (int64_t)kThreads + threadIdx.x; c < n; c += stride) {
+    uint32_t k = (uint32_t)jcolor[c];
+    if (k >= (uint32_t)C) k = (uint32_t)C;
+    keys[c] = k;
+    vals[c] = (int32_t)c;
+  }
+}
+
 // Warp-ballot compaction of the columns into per-colour lists: every warp takes 32 consecutive columns, lanes with
 // the same colour form a group (match.any), the group's leader reserves `popc` slots in that colour's segment with one
 // atomic, each lane writes at its rank inside the group.  Order inside a segment follows reservation order (close to

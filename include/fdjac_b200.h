@@ -285,6 +285,21 @@ fdb_status fdb_sync_set_peers(fdb_sync *sync, void *const *d_flags_by_rank);
 fdb_status fdb_sync_barrier(fdb_sync *sync, void *stream);
 fdb_status fdb_sync_destroy(fdb_sync *sync);
 
+/* ---- Colouring on the device: the ArrayInterface.matrix_colors(A) step callers run before this path
+ *      (test/coloring_tests.jl:112,117).  d_colorvec is a caller-owned DEVICE array of n Int64 (1-based colours), ready to
+ *      be passed to fdb_plan_create_* — a solver that resize!s its problem can recolour and re-plan without a host round
+ *      trip of the pattern.
+ *        banded   closed form ArrayInterface uses for BandedMatrix / Tridiagonal (l=u=1) / Bidiagonal: cycle 1:(l+u+1)
+ *        csc      a valid distance-2 colouring of the columns (no two columns of one colour share a row) by a
+ *                 deterministic Jones-Plassmann sweep; the result depends on the pattern alone.  colptr / rowval: Int64,
+ *                 1-based, host or device.  n_colors / n_rounds (host, nullable) receive maximum(colorvec) / sweeps.
+ *        check    number of (row, colour) collisions of a colouring (0 = valid for this path's decompression). */
+fdb_status fdb_matrix_colors_banded(int64_t n, int64_t l, int64_t u, int64_t *d_colorvec, void *stream);
+fdb_status fdb_matrix_colors_csc(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, int64_t *d_colorvec,
+                                 int64_t *n_colors, int64_t *n_rounds);
+fdb_status fdb_check_coloring_csc(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, const int64_t *colorvec,
+                                  int64_t *n_conflicts);
+
 /* ---- Jacobian-vector product: finite_difference_jvp!(jvp, f, x, v, cache::JVPCache, f_in; relstep, absstep, dir)
  *      src/jvp.jl:238-274 — eps from sqrt(abs(dot(x, v))) (computed on the device), forward: f(fx1,x), f(jvp,x+eps v);
  *      central: f(fx1, x-eps v) then f(jvp, x+eps v).  opts->fdtype selects forward/central (complex is rejected like
