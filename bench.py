@@ -610,7 +610,7 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
         return gpu_arm_multi(args, pkg, dev, rank, world)
     workload, fdtype = args.workload, args.fdtype
-    rec, prob, plan, nnz = run_single(pkg, workload, fdtype, dev, args, args.steps, spin_s=0.6, strategy=args.strategy,
+    rec, prob, plan, nnz = run_single(pkg, workload, fdtype, dev, args, args.steps, spin_s=args.spin, strategy=args.strategy,
                                       sample_clocks=True)
     clk = rec.pop("clocks")
     J, f, x = prob["J"], prob["f"], prob["x"]
@@ -671,7 +671,7 @@ def gpu_arm(args):
                 ("c5_central", "c5", "central", 3, 0)]
         for key, w, fd, st, strat in todo:
             try:
-                r2, p2, pl2, _ = run_single(pkg, w, fd, dev, args, st, strategy=strat)
+                r2, p2, pl2, _ = run_single(pkg, w, fd, dev, args, st, strategy=strat, sample_clocks=True)
                 others[key] = r2
                 del p2, pl2
             except Exception as e:  # an extra must never cost the headline line
@@ -762,7 +762,7 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
     first_call_ms = (time.perf_counter() - t_first) * 1e3
     plan = cache._last_plan
     clocks = Clocks(dev.index) if rank == 0 else None
-    m = measure(pkg, step, plan, args.steps, args.warmup, barrier, dist_max=dist_max, spin_s=0.6)
+    m = measure(pkg, step, plan, args.steps, args.warmup, barrier, dist_max=dist_max, spin_s=args.spin)
     clk = clocks.stop() if clocks else None
     info = plan.info()
     nnz = prob["nnz"]
@@ -923,6 +923,7 @@ def main():
                     help="N>1: how the ranks are ordered around a Jacobian — fdb_sync (device-side flags, default) or an NCCL all_reduce")
     ap.add_argument("--shard", default="colors", choices=["colors", "columns"],
                     help="N>1: colour set (c4) or contiguous column blocks with a slice-aware f! (c2)")
+    ap.add_argument("--spin", type=float, default=0.6, help="seconds of extra warm-up of the same step (lets the 100 ms clock sampler see the load; 0 under ncu)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false",

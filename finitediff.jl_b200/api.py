@@ -60,8 +60,25 @@ def compute_epsilon(fdtype, x: float, relstep: float, absstep: float, dir: float
 
 
 # ------------------------------------------------------------------------------------------------ array helpers
+class PeerValues:
+    """J value storage that lives in ANOTHER process / on another GPU and is only mapped here (CUDA IPC, peer access): a
+    raw device pointer + length, deliberately NOT a torch tensor — torch would attribute the mapping to the exporting
+    device and copy it on any device mismatch, and stores into a copy never reach the owner."""
+    is_cuda = True
+    dtype = torch.float64
+
+    def __init__(self, ptr: int, numel: int):
+        self._ptr, self._numel = int(ptr), int(numel)
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def numel(self) -> int:
+        return self._numel
+
+
 def _is_cuda(t) -> bool:
-    return isinstance(t, torch.Tensor) and t.is_cuda
+    return (isinstance(t, torch.Tensor) and t.is_cuda) or isinstance(t, PeerValues)
 
 
 def _index_ptr(a):

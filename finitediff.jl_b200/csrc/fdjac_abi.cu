@@ -382,6 +382,7 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   // two output buffers + a side stream: a group's scatter (and its NVLink stores, when peers are set) overlaps the next
   // group's f! evaluations
   P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs;
+  { const char *off = getenv("FDB_NO_OVERLAP"); if (off && off[0] == '1') P->double_buffer = false; }   // A/B switch (profiles/)
   const size_t nbuf = P->double_buffer ? 2 : 1;
   if (P->double_buffer) {
     CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
@@ -1389,6 +1390,11 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.write_invalid_zero = (g == 0 && P->rank == 0 && P->has_invalid) ? 1 : 0;
       a.ldF = sF; a.E = P->E;
       a.j_aligned = (reinterpret_cast<uintptr_t>(J) & 15) == 0 && P->peers_aligned;
+      {
+        // random patterns (mean row jump beyond a few cache lines): slab gathers are read-once
+        const char *hs = getenv("FDB_HI_STREAM");
+        a.hi_stream = hs ? (hs[0] == '1') : (P->mean_row_jump > 4096.0);
+      }
       const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
       ScatterTimer tm(P, s);
       if (ident) {
@@ -1412,7 +1418,27 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
           }
         } else if (full) {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);
+          // experiment (FDB_L2_PERSIST_FX=1, profiles/): pin f(x) — re-read by every colour — in L2 for this launch
+          const char *pe = getenv("FDB_L2_PERSIST_FX");
+          const bool persist = pe && pe[0] == '1' && MODE == kForward && a.hi_stream;
+          if (persist) {
+            static bool limit_set = false;
+            if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)64 << 20); limit_set = true; }
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = const_cast<double *>(vfx);
+            av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)P->m * 8, (size_t)64 << 20);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+          }
           diff_scatter_ident<CT, MODE, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
+          if (persist) {
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.num_bytes = 0;
+            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();
+          }
         } else {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, false, kScatterMinBlocks>, sm, tiles);
           diff_scatter_ident<CT, MODE, false, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);

@@ -53,6 +53,8 @@ struct ScatterArgs {
   int32_t l0, G;             // this launch covers local colours [l0, l0+G)
   int32_t write_invalid_zero;// entries whose column has no valid colour get 0 (fill_matrix! semantics)
   int32_t j_aligned;         // J (and every peer) 16-byte aligned
+  int32_t hi_stream;         // random patterns: the slab gathers are read-once -> evict-first loads, so that they do not
+                             // push f(x) (re-read by every colour) out of L2
   int64_t ldF;
   int64_t E;
 };
@@ -111,6 +113,11 @@ __device__ __forceinline__ bool ident_value(const ScatterArgs &a, const ScatterT
     v = 0.0;
     if (k >= (uint32_t)a.C) return true;            // column without a valid colour: stays 0 (fill_matrix!)
     const double e = t.eps ? t.eps[k] : __ldg(a.eps + k);
+    if (MODE == kForward && a.hi_stream) {
+      const double d = __ldcs(a.Fp + (int64_t)k * a.ldF + r) - __ldg(a.fx + r);
+      v = d / e;
+      return true;
+    }
     v = fd_quotient<MODE>(a.Fp + (int64_t)k * a.ldF, MODE == kCentral ? a.Fm + (int64_t)k * a.ldF : a.fx, r, e);
     return true;
   }

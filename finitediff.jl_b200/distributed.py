@@ -344,8 +344,9 @@ class ShardedJacobian:
                 with torch.cuda.device(self.device):
                     L.check(L.lib().fdb_ipc_open(handles[0], C.byref(p)))
                 self._root_ptr = p.value
-                root_vals = torch.as_tensor(api._DevArray(self._root_ptr, (nnz,)), device=self.device)
-                self._J_run = api.SparseMatrixCSC(self.J.m, self.J.n, self.J.colptr, self.J.rowval, root_vals)
+                # rank 0's nzval as mapped into this process: a raw pointer (api.PeerValues), never a torch tensor
+                self._J_run = api.SparseMatrixCSC(self.J.m, self.J.n, self.J.colptr, self.J.rowval,
+                                                  api.PeerValues(self._root_ptr, nnz))
         else:
             self._ipc = IpcBuffer(nnz, self.device)
             self._ipc.tensor.copy_(self.J.nzval)

@@ -3,7 +3,7 @@
 # Usage: bash profiles/launches.sh <tag> <bench args...>    -> gpurun_out/<tag>.csv
 TAG=$1; shift
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}.csv \
-    python bench.py "$@" --steps 2 --warmup 3 --no-cpu --no-e2e --no-graph > gpurun_out/${TAG}.log 2>&1
+    python bench.py "$@" --steps 2 --warmup 3 --no-cpu --no-e2e --no-graph --spin 0 > gpurun_out/${TAG}.log 2>&1
 python - "$TAG" <<'PY'
 import csv, collections, sys
 rows = list(csv.reader(l for l in open(f"gpurun_out/{sys.argv[1]}.csv") if l.startswith('"')))

@@ -250,38 +250,58 @@ def test_group_python_callables(pkg, fdist, oracle):
     g.close()
 
 
+_BARRIER_SCRIPT = r"""
+import ctypes as C, sys
+sys.path.insert(0, {root!r})
+import torch, _bootstrap
+pkg = _bootstrap.load_package()
+L = pkg._lib
+lib = L.lib()
+dev = torch.device("cuda:0")
+hs, flags = [], []
+for r in range(2):
+    h = C.c_void_p()
+    L.check(lib.fdb_sync_create(C.byref(h), r, 2, 0))
+    p = C.c_void_p()
+    L.check(lib.fdb_sync_flags(h, C.byref(p)))
+    hs.append(h)
+    flags.append(p.value)
+for r in range(2):
+    arr = (C.c_void_p * 2)(flags[0], flags[1])
+    L.check(lib.fdb_sync_set_peers(hs[r], arr))
+s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+payload = torch.zeros(2, dtype=torch.float64, device=dev)
+seen = torch.zeros(2, dtype=torch.float64, device=dev)
+torch.cuda.synchronize()
+for it in range(1, 6):
+    with torch.cuda.stream(s0):
+        payload[0:1].fill_(float(it))
+        L.check(lib.fdb_sync_barrier(hs[0], C.c_void_p(s0.cuda_stream)))
+        seen[0:1].copy_(payload[1:2])           # rank 0 reads what rank 1 wrote before ITS barrier
+        L.check(lib.fdb_sync_barrier(hs[0], C.c_void_p(s0.cuda_stream)))
+    with torch.cuda.stream(s1):
+        payload[1:2].fill_(float(10 * it))
+        L.check(lib.fdb_sync_barrier(hs[1], C.c_void_p(s1.cuda_stream)))
+        seen[1:2].copy_(payload[0:1])
+        L.check(lib.fdb_sync_barrier(hs[1], C.c_void_p(s1.cuda_stream)))
+    torch.cuda.synchronize()
+    assert seen.tolist() == [10.0 * it, float(it)], seen.tolist()
+for h in hs:
+    L.check(lib.fdb_sync_destroy(h))
+print("barrier-ok")
+"""
+
+
 def test_device_barrier_two_ranks_one_process(pkg):
     """fdb_sync: two ranks in one process on two streams — each barrier kernel signals the other rank's flag block and
-    waits for its own; ordering is checked through a payload written before the barrier."""
-    L = pkg._lib
-    lib = L.lib()
-    dev = torch.device("cuda:0")
-    hs, flags = [], []
-    for r in range(2):
-        h = C.c_void_p()
-        L.check(lib.fdb_sync_create(C.byref(h), r, 2, 0))
-        p = C.c_void_p()
-        L.check(lib.fdb_sync_flags(h, C.byref(p)))
-        hs.append(h)
-        flags.append(p.value)
-    for r in range(2):
-        arr = (C.c_void_p * 2)(flags[0], flags[1])
-        L.check(lib.fdb_sync_set_peers(hs[r], arr))
-    s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    payload = torch.zeros(2, dtype=torch.float64, device=dev)
-    seen = torch.zeros(2, dtype=torch.float64, device=dev)
-    for it in range(1, 6):
-        with torch.cuda.stream(s0):
-            payload[0:1].fill_(float(it))
-            L.check(lib.fdb_sync_barrier(hs[0], C.c_void_p(s0.cuda_stream)))
-            seen[0:1].copy_(payload[1:2])           # rank 0 reads what rank 1 wrote before ITS barrier
-            L.check(lib.fdb_sync_barrier(hs[0], C.c_void_p(s0.cuda_stream)))
-        with torch.cuda.stream(s1):
-            payload[1:2].fill_(float(10 * it))
-            L.check(lib.fdb_sync_barrier(hs[1], C.c_void_p(s1.cuda_stream)))
-            seen[1:2].copy_(payload[0:1])
-            L.check(lib.fdb_sync_barrier(hs[1], C.c_void_p(s1.cuda_stream)))
-        torch.cuda.synchronize()
-        assert seen.tolist() == [10.0 * it, float(it)]
-    for h in hs:
-        L.check(lib.fdb_sync_destroy(h))
+    waits for its own; ordering is checked through a payload written before the barrier.  Run in a fresh process with
+    CUDA_DEVICE_MAX_CONNECTIONS=32: a barrier kernel SPINS until its peer has signalled, so the two streams must not share
+    a hardware work queue (in a real job the ranks are separate processes / GPUs and cannot queue behind each other)."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    r = subprocess.run([sys.executable, "-c", _BARRIER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "barrier-ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
