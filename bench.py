@@ -912,8 +912,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--fdtype", default=None, choices=["forward", "central", "complex"])
     ap.add_argument("--max-batch", type=int, default=1, dest="max_batch")
-    ap.add_argument("--strategy", type=int, default=0, choices=[0, 1, 2],
-                    help="CSC scatter: 0 auto, 1 fused storage-order pass, 2 colour-major lists per group")
+    ap.add_argument("--strategy", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="CSC scatter: 0 auto, 1 fused storage-order pass, 2 colour-major lists per group, 3 colour-major lists, one launch")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch eagerly instead of replaying the captured CUDA graph of the call")
     ap.add_argument("--gather", default="root", choices=["all", "root", "all_p2p", "none"],

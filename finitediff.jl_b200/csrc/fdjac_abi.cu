@@ -129,9 +129,11 @@ struct fdb_plan {
   // column lists launched right after the colour's f! (random patterns: the slab is gathered from L2; multi-GPU)
   int strategy = 0;
   bool strategy_auto = true;
+  bool lists_resident = false;         // strategy 1 with every local colour's f! output resident: ONE launch over the lists
   bool double_buffer = false;          // two output buffers so a group's scatter overlaps the next group's f!
   cudaStream_t side = nullptr;
   cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_scat[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_eps = nullptr;   // forward mode: the eps pass runs beside f(x) on the side stream
   int32_t *colptr32 = nullptr, *cols_by_color = nullptr;
   // colour-major entry lists of this rank's colours (strategy 1; built by build_cm_lists)
   int32_t *cm_row = nullptr;
@@ -364,11 +366,12 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   int64_t slabs = std::max<int64_t>(1, budget / per_slab);
   slabs = std::min<int64_t>(slabs, std::max<int64_t>(n_local, 1));
   if (P->sp_kind == SP_CSC && P->strategy == 0 && P->strategy_auto && slabs < n_local) P->strategy = 1;
-  if (P->strategy == 1) {
+  if (P->strategy == 1 && !P->lists_resident) {
     // per-colour lists: keep only as many f! outputs in flight as stay L2-resident until their scatter (~48 MB)
     const int64_t l2_slabs = std::max<int64_t>(1, (int64_t)48000000 / per_slab);
-    slabs = std::min<int64_t>(std::min<int64_t>(slabs, l2_slabs), kCmMaxGroup);
+    slabs = std::min<int64_t>(slabs, l2_slabs);
   }
+  if (P->strategy == 1) slabs = std::min<int64_t>(slabs, kCmMaxGroup);
   P->slabs = slabs;
   P->n_groups = n_local == 0 ? 0 : (n_local + slabs - 1) / slabs;
   int64_t batch = (o && o->max_batch > 1) ? o->max_batch : 1;
@@ -381,11 +384,16 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   P->pbatch = pbatch;
   // two output buffers + a side stream: a group's scatter (and its NVLink stores, when peers are set) overlaps the next
   // group's f! evaluations
-  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs;
+  // (one GPU: the scatter and the next f! compete for the same L2 / DRAM — measured on C4, r2: 14.06 ms overlapped vs
+  //  13.08 ms in sequence; with several ranks the scatter's NVLink stores are latency the next f! hides)
+  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && P->world > 1 && (int64_t)P->local_colors.size() > slabs;
+  { const char *on = getenv("FDB_FORCE_OVERLAP"); if (on && on[0] == '1' && P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs) P->double_buffer = true; }
   { const char *off = getenv("FDB_NO_OVERLAP"); if (off && off[0] == '1') P->double_buffer = false; }   // A/B switch (profiles/)
   const size_t nbuf = P->double_buffer ? 2 : 1;
+  CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&P->ev_eps, cudaEventDisableTiming));
   if (P->double_buffer) {
-    CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) {
       CU(cudaEventCreateWithFlags(&P->ev_f[b], cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&P->ev_scat[b], cudaEventDisableTiming));
@@ -568,7 +576,7 @@ static fdb_status try_stage_plan(fdb_plan *P) {
   unsigned int span = 0;
   CU(cudaMemcpy(&span, d_span, 4, cudaMemcpyDeviceToHost));
   const int64_t W = ((int64_t)span + 1) & ~(int64_t)1;
-  const size_t smem = (size_t)kStages * nwin * W * 8 + kStages * 8 + (size_t)P->C * 8;
+  const size_t smem = (size_t)2 * nwin * W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
   if (span == 0 || span > 65535 || smem > (size_t)kStageMaxSmem) return FDB_OK;   // not row-local enough: keep the gather form
   P->stage_W = (int32_t)W;
   P->staged = true;
@@ -626,6 +634,8 @@ static void free_plan(fdb_plan *P) {
   if (P->hstream) cudaStreamDestroy(P->hstream);
   if (P->side) cudaStreamDestroy(P->side);
   for (int b = 0; b < 2; ++b) { if (P->ev_f[b]) cudaEventDestroy(P->ev_f[b]); if (P->ev_scat[b]) cudaEventDestroy(P->ev_scat[b]); }
+  if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  if (P->ev_eps) cudaEventDestroy(P->ev_eps);
   if (P->graph_exec) cudaGraphExecDestroy(P->graph_exec);
   if (P->cstream) cudaStreamDestroy(P->cstream);
   delete P;
@@ -784,8 +794,6 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     }
     P->bucket_start.assign((size_t)C + 2, 0);
     for (int32_t k = 0; k <= C; ++k) P->bucket_start[(size_t)k + 1] = P->bucket_start[(size_t)k] + (int64_t)bc[(size_t)k];
-    std::vector<unsigned long long> cursor(P->bucket_start.begin(), P->bucket_start.begin() + C + 1);
-    cudaMemcpy(d_bucket, cursor.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice);
     PLAN_TRY(build_color_lists(P));
     if (nnz > 1) {
       row_jump_sum<<<P->grid(nnz), kThreads>>>(P->row32, nnz, d_jump);
@@ -805,7 +813,8 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     const int want = opts ? opts->strategy : 0;
     bool per_color = P->world > 1;
     if (want == 1) per_color = false;
-    if (want == 2) per_color = true;
+    if (want == 2 || want == 3) per_color = true;
+    P->lists_resident = want == 3;       // colour-major lists, all slabs resident, one launch at the end
     P->strategy = per_color ? 1 : 0;
     P->strategy_auto = want == 0;
   }
@@ -1242,9 +1251,18 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   //  here would race with the peers' stores.
   const bool self_defining = (ident || band_data) && n_local > 0;
   if (!self_defining && P->n_peers == 0 && !P->shared_J && P->j_len > 0) TRY(zero_J(P, J, s));
+  // forward mode without f_in: f(x) (jacobians.jl:541) and the step-size pass are independent — the eps kernels run on the
+  // side stream beside the user's f(x) and are joined before the first perturbation (a parallel branch of the CUDA graph)
+  bool eps_beside_fx = MODE == kForward && !f_in && !P->ext_eps && P->side && P->ev_fork && P->C > 0;
+  { const char *off = getenv("FDB_NO_EPS_OVERLAP"); if (off && off[0] == '1') eps_beside_fx = false; }
   if (P->ext_eps) {
     // sharded runs: the step sizes of the FULL x come from outside (fdb_color_eps on the full vector)
     if (P->C > 0) CU(cudaMemcpyAsync(P->eps, P->ext_eps, (size_t)P->C * 8, cudaMemcpyDeviceToDevice, s));
+  } else if (eps_beside_fx) {
+    CU(cudaEventRecord(P->ev_fork, s));
+    CU(cudaStreamWaitEvent(P->side, P->ev_fork, 0));
+    TRY(run_eps<CT>(P, x, relstep, absstep, dir, P->side));
+    CU(cudaEventRecord(P->ev_eps, P->side));
   } else {
     TRY(run_eps<CT>(P, x, relstep, absstep, dir, s));
   }
@@ -1253,6 +1271,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     if (f_in) vfx = f_in;                                  // jacobians.jl:543-544
     else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; } // :541-542
   }
+  if (eps_beside_fx) CU(cudaStreamWaitEvent(s, P->ev_eps, 0));
   // build the perturbed points of local colours [li0, li0+kc) into the point buffers (one pass over x per 4 colours)
   auto perturb_window = [&](int64_t li0, int64_t kc) -> fdb_status {
       for (int64_t q0 = 0; q0 < kc; q0 += kPerturbMaxPoints) {
@@ -1412,33 +1431,23 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             sa.fx = vfx; sa.Fp = P->Fp; sa.Fm = P->Fm; sa.eps = P->eps; sa.J = J; sa.C = P->C; sa.W = P->stage_W;
             sa.ldF = sF; sa.src_len = P->ldF; sa.E = P->E; sa.j_aligned = a.j_aligned;
             const int nwin = CENTRAL ? 2 * P->C : P->C + 1;
-            const size_t ssm = (size_t)kStages * nwin * P->stage_W * 8 + kStages * 8 + (size_t)P->C * 8;
-            const int grid = resident_grid(P, diff_scatter_staged<CT, MODE>, ssm, tiles);
-            diff_scatter_staged<CT, MODE><<<grid, kThreads, ssm, s>>>(sa);
+            const char *st_env = getenv("FDB_STAGES");
+            int stages = st_env && st_env[0] == '3' ? 3 : 2;
+            if ((size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;
+            sa.stages = stages;
+            const size_t ssm = (size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
+            const char *mb_env = getenv("FDB_STAGED_MINB");
+            if (mb_env && mb_env[0] == '8') {
+              const int grid = resident_grid(P, diff_scatter_staged<CT, MODE, 8>, ssm, tiles);
+              diff_scatter_staged<CT, MODE, 8><<<grid, kThreads, ssm, s>>>(sa);
+            } else {
+              const int grid = resident_grid(P, diff_scatter_staged<CT, MODE, 6>, ssm, tiles);
+              diff_scatter_staged<CT, MODE, 6><<<grid, kThreads, ssm, s>>>(sa);
+            }
           }
         } else if (full) {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);
-          // experiment (FDB_L2_PERSIST_FX=1, profiles/): pin f(x) — re-read by every colour — in L2 for this launch
-          const char *pe = getenv("FDB_L2_PERSIST_FX");
-          const bool persist = pe && pe[0] == '1' && MODE == kForward && a.hi_stream;
-          if (persist) {
-            static bool limit_set = false;
-            if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)64 << 20); limit_set = true; }
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = const_cast<double *>(vfx);
-            av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)P->m * 8, (size_t)64 << 20);
-            av.accessPolicyWindow.hitRatio = 1.0f;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-          }
           diff_scatter_ident<CT, MODE, true, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);
-          if (persist) {
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.num_bytes = 0;
-            cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-            cudaGetLastError();
-          }
         } else {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, false, kScatterMinBlocks>, sm, tiles);
           diff_scatter_ident<CT, MODE, false, kScatterMinBlocks><<<grid, kThreads, sm, s>>>(a);

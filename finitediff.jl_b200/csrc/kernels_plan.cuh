@@ -255,34 +255,6 @@ color_sort_keys(const CT *__restrict__ jcolor, int64_t n, int32_t C, uint32_t *_
   }
 }
 
-// Warp-ballot compaction of the columns into per-colour lists: every warp takes 32 consecutive columns, lanes with
-// the same colour form a group (match.any), the group's leader reserves `popc` slots in that colour's segment with one
-// atomic, each lane writes at its rank inside the group.  Order inside a segment follows reservation order (close to
-// ascending; the result does not depend on it — every slot of J is written exactly once).
-template <typename CT>
-__global__ void __launch_bounds__(kThreads)
-bucket_columns(const CT *__restrict__ jcolor, int64_t n, int32_t C, unsigned long long *__restrict__ cursor /* [C+1], starts */,
-               int32_t *__restrict__ cols_by_color) {
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  const int lane = threadIdx.x & 31;
-  for (int64_t c0 = (blockIdx.x * (int64_t)kThreads + threadIdx.x) - lane; c0 < n; c0 += stride) {
-    const int64_t c = c0 + lane;
-    const bool in = c < n;
-    uint32_t k = in ? (uint32_t)jcolor[c] : 0xFFFFFFFEu;
-    if (in && k >= (uint32_t)C) k = (uint32_t)C;
-    const unsigned act = __ballot_sync(0xffffffffu, in);
-    if (in) {
-      const unsigned peers = __match_any_sync(act, k);
-      const int leader = __ffs(peers) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(cursor + k, (unsigned long long)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      cols_by_color[base + rank] = (int32_t)c;
-    }
-  }
-}
-
 // ---- colour-major entry lists (diff_scatter_cm) ----
 // list_cols[i] = i-th column of this rank's colour-major order (its local colours one after the other, then — rank 0
 // only — the columns without a valid colour); list_cnt[i] = stored entries of that column.

@@ -46,7 +46,7 @@ __device__ __forceinline__ void fence_mbar_init() {
 }
 
 constexpr int kStageMaxWin = 8;        // windows per tile: C + 1 (forward: slabs + fx) or 2C (central: plus / minus slabs)
-constexpr int kStages = 2;             // tiles in flight per block
+constexpr int kStagesMax = 3;          // tiles in flight per block (2 by default: 8 blocks/SM; 3 leaves 6)
 constexpr int kStageMaxSmem = 46 * 1024;
 
 struct StagedArgs {
@@ -57,6 +57,7 @@ struct StagedArgs {
   const double *fx, *Fp, *Fm, *eps;
   double *J;
   int32_t C, W;              // colours (slab == colour), window length in rows (even)
+  int32_t stages;            // 2 or 3
   int64_t ldF, src_len;      // slab stride; readable doubles behind fx / every slab (even)
   int64_t E;
   int32_t j_aligned;
@@ -104,17 +105,20 @@ stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__rest
   }
 }
 
-template <typename CT, int MODE>
-__global__ void __launch_bounds__(kThreads, kScatterMinBlocks)
+// MINB: resident blocks per SM the register budget is cut for (8 -> 32 registers, 6 -> 40: no spill of the prefetched
+// index registers; with TMA doing the wide loads the kernel needs fewer resident warps than the gather form)
+template <typename CT, int MODE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_staged(const StagedArgs a) {
   static_assert(MODE == kForward || MODE == kCentral, "staged scatter: forward / central");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = a.C, W = a.W;
   const int nwin = MODE == kCentral ? 2 * C : C + 1;
   const int stage_elems = nwin * W;
-  double *buf = reinterpret_cast<double *>(smem_raw);                       // [kStages][nwin][W]
+  const int kStages = a.stages;
+  double *buf = reinterpret_cast<double *>(smem_raw);                       // [stages][nwin][W]
   uint64_t *full = reinterpret_cast<uint64_t *>(buf + kStages * stage_elems);
-  double *s_eps = reinterpret_cast<double *>(full + kStages);               // [C]
+  double *s_eps = reinterpret_cast<double *>(full + kStagesMax);            // [C]
   const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
   const int64_t nfull = a.E / kTile;
   constexpr int kHalf = kTile / 2;
@@ -158,19 +162,30 @@ diff_scatter_staged(const StagedArgs a) {
     return d / (MODE == kCentral ? 2 * e : e);
   };
 
-  uint32_t it = 0;
-  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, ++it) {
-    const int s = (int)(it & 1u);
-    const uint32_t parity = (it >> 1) & 1u;
+  // index pairs of a tile: coalesced, independent of the staged data — loaded ONE TILE AHEAD (software pipelining), so
+  // their latency overlaps the previous tile's wait + arithmetic instead of following the block barrier
+  struct Idx { ushort2 ra, rb; uint32_t ka0, ka1, kb0, kb1; };
+  auto load_idx = [&](int64_t tile) {
+    Idx x;
     const uint16_t *__restrict__ rt = a.row16 + tile * kTile;
     const CT *__restrict__ ct = ecolor + tile * kTile;
+    x.ra = __ldcs(reinterpret_cast<const ushort2 *>(rt + tid2));
+    x.rb = __ldcs(reinterpret_cast<const ushort2 *>(rt + kHalf + tid2));
+    ld_color_pair<CT>(ct + tid2, x.ka0, x.ka1);
+    ld_color_pair<CT>(ct + kHalf + tid2, x.kb0, x.kb1);
+    return x;
+  };
+  uint32_t it = 0;
+  int s = 0;
+  uint32_t parity = 0;
+  Idx nx{};
+  if ((int64_t)blockIdx.x < nfull) nx = load_idx(blockIdx.x);
+  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, ++it) {
     double *__restrict__ Jt = a.J + tile * kTile;
-    // this tile's index pairs: coalesced, independent of the staged data
-    const ushort2 ra = __ldcs(reinterpret_cast<const ushort2 *>(rt + tid2));
-    const ushort2 rb = __ldcs(reinterpret_cast<const ushort2 *>(rt + kHalf + tid2));
-    uint32_t ka0, ka1, kb0, kb1;
-    ld_color_pair<CT>(ct + tid2, ka0, ka1);
-    ld_color_pair<CT>(ct + kHalf + tid2, kb0, kb1);
+    const Idx cur = nx;
+    if (tile + gridDim.x < nfull) nx = load_idx(tile + gridDim.x);
+    const ushort2 ra = cur.ra, rb = cur.rb;
+    const uint32_t ka0 = cur.ka0, ka1 = cur.ka1, kb0 = cur.kb0, kb1 = cur.kb1;
     while (!mbar_try_wait(full + s, parity)) {}
     const double *__restrict__ win = buf + s * stage_elems;
     const double va0 = value(win, ra.x, ka0), va1 = value(win, ra.y, ka1);
@@ -186,6 +201,7 @@ diff_scatter_staged(const StagedArgs a) {
       const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
       if (nxt < nfull) issue(nxt, s);
     }
+    if (++s == kStages) { s = 0; parity ^= 1u; }
   }
   // the last, partial tile (E % kTile entries): gather form, one block
   const int64_t rem0 = nfull * kTile;

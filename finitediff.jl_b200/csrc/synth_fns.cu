@@ -69,30 +69,6 @@ __global__ void __launch_bounds__(kT) k_ellrows(double *__restrict__ fx, const d
   }
 }
 
-// K known at compile time: all 2K streaming loads of a row are issued first, then its K gathers from x (L2-resident), then the
-// sums in the SAME left-to-right order as the generic kernel / the CPU twin — one latency chain per row instead of K
-// (the generic loop cannot be unrolled by the compiler: 5*10^6 rows x 8 dependent (index -> gather) round trips)
-template <int K>
-__global__ void __launch_bounds__(kT) k_ellrows_k(double *__restrict__ fx, const double *__restrict__ x, int64_t m,
-                                                  const int32_t *__restrict__ cols, const double *__restrict__ coef,
-                                                  int64_t ldfx, int64_t ldx) {
-  const double *xb = x + (int64_t)blockIdx.y * ldx;
-  double *fb = fx + (int64_t)blockIdx.y * ldfx;
-  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < m; i += (int64_t)gridDim.x * kT) {
-    int32_t c[K];
-    double a[K], v[K];
-#pragma unroll
-    for (int p = 0; p < K; ++p) { c[p] = __ldcs(cols + (int64_t)p * m + i); a[p] = __ldcs(coef + (int64_t)p * m + i); }
-#pragma unroll
-    for (int p = 0; p < K; ++p) v[p] = __ldg(xb + c[p]);
-    double s = mul(a[0], v[0]);
-#pragma unroll
-    for (int p = 1; p < K; ++p) s = add(s, mul(a[p], v[p]));
-    s = add(s, mul(0.1, mul(v[0], v[0])));
-    fb[i] = s;
-  }
-}
-
 // blocked sum: blocks of 1024 summed sequentially (one thread each — tiny), then block sums sequentially
 __global__ void __launch_bounds__(kT) k_block_sums(const double *__restrict__ x, int64_t n, int64_t ldx,
                                                    double *__restrict__ bs, int64_t nblk) {
@@ -256,8 +232,7 @@ int fdbs_ellrows(void *vctx, double *d_fx, const double *d_x, int64_t batch, int
   c->calls += batch;
   if (c->m <= 0) return 0;
   dim3 grid((unsigned)blocks_for(c->m, 148 * 16), (unsigned)batch);
-  if (c->K == 8) k_ellrows_k<8><<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->m, c->d_cols, c->d_coef, ldfx, ldx);
-  else k_ellrows<<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->m, (int)c->K, c->d_cols, c->d_coef, ldfx, ldx);
+  k_ellrows<<<grid, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->m, (int)c->K, c->d_cols, c->d_coef, ldfx, ldx);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

@@ -86,8 +86,9 @@ typedef struct {
   int32_t rank, world;     /* colour partition over GPUs (one process per GPU): this plan handles the colours
                               owned by `rank` of `world`; world<=1 => all colours */
   int32_t partition;       /* 0: round-robin colours; 1: nnz-balanced (LPT) */
-  int32_t strategy;        /* CSC scatter: 0 auto; 1 one fused pass over J's storage order; 2 per-colour column lists
-                              launched after each colour's f! (see fdb_plan_info_t.strategy) */
+  int32_t strategy;        /* CSC scatter: 0 auto; 1 one fused pass over J's storage order; 2 colour-major entry lists, a
+                              launch per group of L2-resident f! outputs, overlapped with the next group's f!; 3 colour-major
+                              lists with every f! output resident: one launch at the end (see fdb_plan_info_t.strategy) */
   int32_t use_graph;       /* 1: capture the whole call (library kernels + the callback's launches) into a CUDA graph on
                               first use and replay it while (f, ctx, buffers, scalars) stay the same.  The callback must
                               be capture-safe: enqueue-only on the given stream, no allocation, no host-side state. */

@@ -272,6 +272,12 @@ for r in range(2):
 s0, s1 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 payload = torch.zeros(2, dtype=torch.float64, device=dev)
 seen = torch.zeros(2, dtype=torch.float64, device=dev)
+# load every kernel the loop launches BEFORE a barrier kernel can be spinning: with CUDA's lazy module loading the first
+# launch of a kernel synchronises the context, which would wait for the spinning kernel, which waits for the launch
+for st in (s0, s1):
+    with torch.cuda.stream(st):
+        payload[0:1].fill_(0.0)
+        seen[0:1].copy_(payload[1:2])
 torch.cuda.synchronize()
 for it in range(1, 6):
     with torch.cuda.stream(s0):
@@ -296,12 +302,13 @@ def test_device_barrier_two_ranks_one_process(pkg):
     """fdb_sync: two ranks in one process on two streams — each barrier kernel signals the other rank's flag block and
     waits for its own; ordering is checked through a payload written before the barrier.  Run in a fresh process with
     CUDA_DEVICE_MAX_CONNECTIONS=32: a barrier kernel SPINS until its peer has signalled, so the two streams must not share
-    a hardware work queue (in a real job the ranks are separate processes / GPUs and cannot queue behind each other)."""
+    a hardware work queue, and every kernel is loaded up front (lazy module loading synchronises the context).  In a real
+    job the ranks are separate processes / GPUs and cannot queue behind each other."""
     import os
     import subprocess
     import sys
     from pathlib import Path
     root = str(Path(__file__).resolve().parent.parent)
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER")
     r = subprocess.run([sys.executable, "-c", _BARRIER_SCRIPT.format(root=root)], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "barrier-ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
