@@ -556,6 +556,8 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   return FDB_OK;
 }
 
+static const char kStagedDefaultVariant[3] = "6p";
+
 // TMA-staged fused pass: eligible when the whole Jacobian is one resident group on one rank, the destination is the
 // identity (CSC nzval) and every 1024-entry tile touches a short row window (row-local pattern).
 static fdb_status try_stage_plan(fdb_plan *P) {
@@ -1327,6 +1329,8 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     a.row = P->cm_row; a.slot = P->cm_slot; a.seg_start = P->cm_start; a.local_colors = P->d_local_colors;
     a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
     a.l0 = (int32_t)l0; a.G = (int32_t)G; a.ldF = sF;
+    a.m = COMPLEX ? 2 * P->m : P->m;
+    { const char *pf = getenv("FDB_CM_PREFETCH"); a.prefetch_next = (G > 1 && !(pf && pf[0] == '0')) ? 1 : 0; }
     const int64_t tiles = (total + kCmTile - 1) / kCmTile;
     ScatterTimer tm(P, ss);
     if (wide) {
@@ -1436,14 +1440,16 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             if ((size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;
             sa.stages = stages;
             const size_t ssm = (size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
-            const char *mb_env = getenv("FDB_STAGED_MINB");
-            if (mb_env && mb_env[0] == '8') {
-              const int grid = resident_grid(P, diff_scatter_staged<CT, MODE, 8>, ssm, tiles);
-              diff_scatter_staged<CT, MODE, 8><<<grid, kThreads, ssm, s>>>(sa);
-            } else {
-              const int grid = resident_grid(P, diff_scatter_staged<CT, MODE, 6>, ssm, tiles);
-              diff_scatter_staged<CT, MODE, 6><<<grid, kThreads, ssm, s>>>(sa);
-            }
+            // variants (profiles/ A/B; FDB_STAGED_VARIANT = 8n | 6p | 6n): resident blocks per SM x index prefetch
+            const char *v_env = getenv("FDB_STAGED_VARIANT");
+            const char v0 = v_env ? v_env[0] : kStagedDefaultVariant[0], v1 = v_env && v_env[0] ? v_env[1] : kStagedDefaultVariant[1];
+            auto go = [&](auto kern) {
+              const int grid = resident_grid(P, kern, ssm, tiles);
+              kern<<<grid, kThreads, ssm, s>>>(sa);
+            };
+            if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false>);
+            else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false>);
+            else go(diff_scatter_staged<CT, MODE, 6, true>);
           }
         } else if (full) {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);

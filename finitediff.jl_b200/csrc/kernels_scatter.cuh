@@ -230,6 +230,10 @@ struct CmArgs {
   double *const *peers;
   int32_t n_peers;
   int32_t l0, G;               // this launch: local colours [l0, l0+G); slab of local colour li is li - l0
+  int32_t prefetch_next;       // several resident colours in one launch: while the tiles of colour s are processed, the
+                               // grid streams slab s+1 into L2 (prefetch.global.L2, one pass, sequential) — the random
+                               // 8-byte gathers of the next colour then hit L2 instead of fetching a DRAM granule each
+  int64_t m;                   // rows of a slab (prefetch extent)
   int64_t ldF;
 };
 
@@ -263,6 +267,20 @@ diff_scatter_cm(const CmArgs a) {
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_start[mid] <= tile) lo = mid; else hi = mid; }
       seg = lo;
     }
+    if (a.prefetch_next && seg + 1 < a.G) {
+      // this tile's share of the next colour's slab(s): tile j of T in the segment takes lines [j*L, (j+1)*L)
+      const int64_t seg_len = s_start[seg + 1] - s_start[seg];
+      const int64_t T = (seg_len + kCmTile - 1) / kCmTile;
+      const int64_t j = (tile - s_start[seg]) / kCmTile;
+      const int64_t lines = (a.m * 8 + 127) / 128;
+      const int64_t L = (lines + T - 1) / T;
+      const char *nxt = reinterpret_cast<const char *>(a.Fp + (int64_t)(seg + 1) * a.ldF);
+      const char *nxm = MODE == kCentral ? reinterpret_cast<const char *>(a.Fm + (int64_t)(seg + 1) * a.ldF) : nullptr;
+      for (int64_t ln = j * L + threadIdx.x; ln < (j + 1) * L && ln < lines; ln += kThreads) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + ln * 128));
+        if (MODE == kCentral) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxm + ln * 128));
+      }
+    }
     double v[kCmPerThread];
 #pragma unroll
     for (int u = 0; u < kCmPerThread; ++u) {
@@ -272,7 +290,10 @@ diff_scatter_cm(const CmArgs a) {
         while (q >= s_start[seg + 1]) ++seg;
         const double *hi_p = a.Fp + (int64_t)seg * a.ldF;
         const double *lo_p = MODE == kCentral ? a.Fm + (int64_t)seg * a.ldF : a.fx;
-        v[u] = fd_quotient<MODE>(hi_p, lo_p, r[u], s_eps[seg]);            // fused with ext/..SparseArraysExt.jl:44
+        if (MODE == kForward && a.prefetch_next)                             // read-once slab values: evict-first, f(x) stays
+          v[u] = (__ldcs(hi_p + r[u]) - __ldg(lo_p + r[u])) / s_eps[seg];
+        else
+          v[u] = fd_quotient<MODE>(hi_p, lo_p, r[u], s_eps[seg]);          // fused with ext/..SparseArraysExt.jl:44
       }
     }
 #pragma unroll

@@ -107,7 +107,7 @@ stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__rest
 
 // MINB: resident blocks per SM the register budget is cut for (8 -> 32 registers, 6 -> 40: no spill of the prefetched
 // index registers; with TMA doing the wide loads the kernel needs fewer resident warps than the gather form)
-template <typename CT, int MODE, int MINB>
+template <typename CT, int MODE, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_staged(const StagedArgs a) {
   static_assert(MODE == kForward || MODE == kCentral, "staged scatter: forward / central");
@@ -179,11 +179,11 @@ diff_scatter_staged(const StagedArgs a) {
   int s = 0;
   uint32_t parity = 0;
   Idx nx{};
-  if ((int64_t)blockIdx.x < nfull) nx = load_idx(blockIdx.x);
+  if (PREFETCH && (int64_t)blockIdx.x < nfull) nx = load_idx(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, ++it) {
     double *__restrict__ Jt = a.J + tile * kTile;
-    const Idx cur = nx;
-    if (tile + gridDim.x < nfull) nx = load_idx(tile + gridDim.x);
+    const Idx cur = PREFETCH ? nx : load_idx(tile);
+    if (PREFETCH && tile + gridDim.x < nfull) nx = load_idx(tile + gridDim.x);
     const ushort2 ra = cur.ra, rb = cur.rb;
     const uint32_t ka0 = cur.ka0, ka1 = cur.ka1, kb0 = cur.kb0, kb1 = cur.kb1;
     while (!mbar_try_wait(full + s, parity)) {}
