@@ -487,8 +487,11 @@ def known_traffic(key):
 
 def scatter_kernel_name(info, fdtype):
     if info["sp_kind"] == 1:
-        return ("diff_scatter_cm<%s>" % fdtype if info["strategy"] == 1
-                else "diff_scatter_ident<u%d,%s%s>" % (info["color_bits"], fdtype, ",FULL" if info["n_groups"] == 1 else ""))
+        if info["strategy"] == 1:
+            return "diff_scatter_cm<%s>" % fdtype
+        if info.get("staged"):
+            return "diff_scatter_staged<u%d,%s> (TMA-staged fused pass)" % (info["color_bits"], fdtype)
+        return "diff_scatter_ident<u%d,%s%s>" % (info["color_bits"], fdtype, ",FULL" if info["n_groups"] == 1 else "")
     return {4: "diff_slabs + diff_scatter_band_flat", 0: "diff_columns", 3: "diff_scatter_dest"}.get(info["sp_kind"], "diff_scatter")
 
 
@@ -579,6 +582,7 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0, 
     f_inv = m["c1"]["f_invocations"] - m["c0"]["f_invocations"]
     f_launch_per_point = {"c5": 2}.get(workload, 1)
     key = f"{workload}_{fdtype}" + ("_lists" if info["sp_kind"] == 1 and info["strategy"] == 1 else "")
+    roof_kernel = scatter_kernel_name(info, fdtype)
     rec = {
         "workload": workload_config(workload, fdtype)["workload"], "ms_per_step": m["ms_step"], "value": nnz / (m["ms_step"] * 1e-3),
         "unit": "nnz/s", "steps": steps, "f_evals_per_s": f_points / (m["ms_total"] * 1e-3), "first_call_ms": first_call_ms,
@@ -586,7 +590,9 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0, 
         "parity": analytic_parity(pkg, workload, fdtype, prob),
         "gpu_launches": int(lib_launches + f_inv * f_launch_per_point),
         "gpu_launches_detail": {"library_kernels": int(lib_launches), "f_callback_invocations": int(f_inv)},
-        "scatter_strategy": {0: "fused storage-order pass", 1: "colour-major lists per group"}[info["strategy"]] if info["sp_kind"] == 1 else None,
+        "scatter_strategy": ({0: "fused storage-order pass" + (" (TMA-staged)" if "staged" in roof_kernel else ""),
+                              1: "colour-major lists, one launch" if info["n_groups"] == 1 else "colour-major lists per group"}[info["strategy"]]
+                             if info["sp_kind"] == 1 else None),
         "scatter_groups": info["n_groups"], "clocks": clk,
     }
     return rec, prob, plan, nnz
@@ -667,7 +673,7 @@ def gpu_arm(args):
         del prob, J, f, x, plan
         torch.cuda.empty_cache()
         todo = [("c2_central", "c2", "central", 100, 0), ("c3_forward", "c3", "forward", 30, 0),
-                ("c4_forward_fused", "c4", "forward", 20, 1), ("c4_forward_lists", "c4", "forward", 20, 2),
+                ("c4_forward_fused", "c4", "forward", 20, 1), ("c4_forward_lists", "c4", "forward", 20, 3),
                 ("c5_central", "c5", "central", 3, 0)]
         for key, w, fd, st, strat in todo:
             try:
@@ -733,7 +739,7 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
         # ---- same-workload 1-GPU reference, rank 0 alone, same run: t1 for the strong-scaling record, J1 for parity
         if rank == 0:
             best = None
-            for strat in (1, 2):
+            for strat in (1, 3):
                 r1, p1, pl1, _ = run_single(pkg, "c4", fdtype, dev, args, max(5, min(args.steps, 20)), strategy=strat)
                 if best is None or r1["ms_per_step"] < best[0]["ms_per_step"]:
                     best = (r1, p1["J"].nzval.clone(), pl1.eps().copy())

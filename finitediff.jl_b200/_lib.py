@@ -39,7 +39,7 @@ class PlanInfo(C.Structure):
         ("fcalls_per_jacobian", C.c_int64), ("device_bytes", C.c_int64),
         ("fdtype", C.c_int32), ("jkind", C.c_int32), ("sp_kind", C.c_int32), ("color_bits", C.c_int32),
         ("alg_bytes_scatter", C.c_int64), ("strategy", C.c_int32), ("lanes", C.c_int32), ("mean_row_jump", C.c_double),
-        ("moved_bytes_scatter", C.c_int64),
+        ("moved_bytes_scatter", C.c_int64), ("staged", C.c_int32), ("lists_resident", C.c_int32),
     ]
 
     def as_dict(self):

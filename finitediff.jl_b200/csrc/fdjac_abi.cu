@@ -556,7 +556,9 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   return FDB_OK;
 }
 
-static const char kStagedDefaultVariant[3] = "6p";
+// r2 A/B on C2 (same box, 1965 MHz, scatter us forward / central): gather form 123.4 / 139.5; staged 8 blocks 112.5 / 137.5;
+// 6 blocks + index prefetch 108.0 / 139.0; 6 blocks, no prefetch 105.6 / 130.6 (kept)
+static const char kStagedDefaultVariant[3] = "6n";
 
 // TMA-staged fused pass: eligible when the whole Jacobian is one resident group on one rank, the destination is the
 // identity (CSC nzval) and every 1024-entry tile touches a short row window (row-local pattern).
@@ -817,6 +819,10 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     if (want == 1) per_color = false;
     if (want == 2 || want == 3) per_color = true;
     P->lists_resident = want == 3;       // colour-major lists, all slabs resident, one launch at the end
+    // auto, one GPU, random pattern with many colours: colour-major lists with every slab resident (one launch) — the
+    // colour-by-colour order keeps the gathers of a launch phase inside one 8m-byte slab + f(x) instead of spreading them
+    // over C slabs at once (C4, r2: 0.96 ms vs 1.18 ms for the storage-order pass; row-local patterns stay fused / staged)
+    if (want == 0 && P->world == 1 && P->mean_row_jump > 4096.0 && C >= 16) { per_color = true; P->lists_resident = true; }
     P->strategy = per_color ? 1 : 0;
     P->strategy_auto = want == 0;
   }
@@ -1031,6 +1037,8 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
   info->strategy = P->strategy;
   info->lanes = P->lanes;
   info->mean_row_jump = P->mean_row_jump;
+  info->staged = P->staged ? 1 : 0;
+  info->lists_resident = P->lists_resident ? 1 : 0;
   {
     // compulsory bytes of the formulation that runs (see the header); slabs read per entry: 1 (forward / complex), 2 (central)
     const int64_t ct = P->color_bits / 8;
@@ -1330,7 +1338,9 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
     a.l0 = (int32_t)l0; a.G = (int32_t)G; a.ldF = sF;
     a.m = COMPLEX ? 2 * P->m : P->m;
-    { const char *pf = getenv("FDB_CM_PREFETCH"); a.prefetch_next = (G > 1 && !(pf && pf[0] == '0')) ? 1 : 0; }
+    // (software L2 prefetch of the next colour's slab: measured SLOWER on C4 — 1.255 vs 0.962 ms — the 40 MB slab, the next
+    //  one and f(x) do not fit the L2 together; off unless FDB_CM_PREFETCH=1)
+    { const char *pf = getenv("FDB_CM_PREFETCH"); a.prefetch_next = (G > 1 && pf && pf[0] == '1') ? 1 : 0; }
     const int64_t tiles = (total + kCmTile - 1) / kCmTile;
     ScatterTimer tm(P, ss);
     if (wide) {
@@ -1448,6 +1458,8 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
               kern<<<grid, kThreads, ssm, s>>>(sa);
             };
             if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false>);
+            else if (v0 == '5') go(diff_scatter_staged<CT, MODE, 5, false>);
+            else if (v0 == '4') go(diff_scatter_staged<CT, MODE, 4, false>);
             else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false>);
             else go(diff_scatter_staged<CT, MODE, 6, true>);
           }

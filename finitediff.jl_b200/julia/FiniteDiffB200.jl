@@ -69,6 +69,8 @@ struct PlanInfo
     lanes::Int32
     mean_row_jump::Float64
     moved_bytes_scatter::Int64
+    staged::Int32
+    lists_resident::Int32
 end
 
 struct FdbError <: Exception

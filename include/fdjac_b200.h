@@ -118,7 +118,11 @@ typedef struct {
   int64_t moved_bytes_scatter; /* COMPULSORY bytes of the shipped diff+scatter formulation per Jacobian (this rank): every
                               index / slab / fx / J byte it must move once — the roofline numerator.  CSC fused pass:
                               E*(4 + |colour| + 8*slabs_read + 8) [+ 8m fx, forward]; colour-major lists: E*(4 + |slot| +
-                              8*slabs_read + 8) [+ 8m]; explicit destinations: + 8 per entry; banded / dense: = alg_bytes */
+                              8*slabs_read + 8) [+ 8m]; explicit destinations: + 8 per entry; banded / dense: = alg_bytes;
+                              TMA-staged fused pass: E*(2 + |colour| + 8) + 8m*(slabs_read*C [+ 1]) */
+  int32_t staged;          /* 1: the fused pass runs in its TMA-staged form (row-local pattern: slab windows staged through
+                              shared memory by cp.async.bulk, 16-bit row offsets) */
+  int32_t lists_resident;  /* 1: colour-major lists with every local colour's f! output resident (one launch) */
 } fdb_plan_info_t;
 
 typedef struct {
