@@ -749,7 +749,7 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
             J1, eps1 = best[1], best[2]
         barrier()
 
-    prob = build_gpu_problem(pkg, workload, fdtype, dev, rank, world, args.max_batch, args.graph)
+    prob = build_gpu_problem(pkg, workload, fdtype, dev, rank, world, args.max_batch, args.graph, strategy=args.strategy)
     J, f, x, cache = prob["J"], prob["f"], prob["x"], prob["cache"]
     sharded = None
     if workload == "c4":
