@@ -11,8 +11,10 @@ if [ "$N" = "2" ]; then
 fi
 run c4            $TR bench.py --gpus $N --steps 20 --warmup 5
 run c4_nooverlap  FDB_NO_OVERLAP=1 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e
+if [ "$N" != "8" ]; then
 run c4_ncclbar    $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e --barrier nccl
 run c4_onelaunch  $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e --strategy 3
+fi
 if [ "$N" = "4" ]; then
   run c5          $TR bench.py --gpus $N --workload c5 --steps 3 --warmup 3
   run c2cols      $TR bench.py --gpus $N --workload c2 --shard columns --gather none --steps 50
