@@ -485,6 +485,16 @@ def known_traffic(key):
     return None, None
 
 
+def traffic_key(workload, fdtype, info):
+    """key into profiles/traffic.json: which ncu capture describes the scatter launches of this plan"""
+    key = f"{workload}_{fdtype}"
+    if info["sp_kind"] == 1 and info["strategy"] == 1:
+        key += "_lists" if info["n_groups"] == 1 else "_lists_per_group"
+    elif info["sp_kind"] == 1 and not info.get("staged"):
+        key += "_gather"
+    return key
+
+
 def scatter_kernel_name(info, fdtype):
     if info["sp_kind"] == 1:
         if info["strategy"] == 1:
@@ -581,7 +591,7 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0, 
     lib_launches = m["c1"]["kernel_launches"] - m["c0"]["kernel_launches"]
     f_inv = m["c1"]["f_invocations"] - m["c0"]["f_invocations"]
     f_launch_per_point = {"c5": 2}.get(workload, 1)
-    key = f"{workload}_{fdtype}" + ("_lists" if info["sp_kind"] == 1 and info["strategy"] == 1 else "")
+    key = traffic_key(workload, fdtype, info)
     roof_kernel = scatter_kernel_name(info, fdtype)
     rec = {
         "workload": workload_config(workload, fdtype)["workload"], "ms_per_step": m["ms_step"], "value": nnz / (m["ms_step"] * 1e-3),
@@ -778,7 +788,7 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
     lib_launches = m["c1"]["kernel_launches"] - m["c0"]["kernel_launches"]
     f_inv = m["c1"]["f_invocations"] - m["c0"]["f_invocations"]
     gpu_launches = lib_launches + f_inv * {"c5": 2}.get(workload, 1)
-    key = f"{workload}_{fdtype}" + ("_lists" if info["sp_kind"] == 1 and info["strategy"] == 1 else "")
+    key = traffic_key(workload, fdtype, info)
     roofline = roofline_record(info, fdtype, m["scat_ms"], m["scat_n"], m["tsteps"], key)
 
     # ---- parity inside the run: analytic sampled check on every rank's result + (c4) sharded == unsharded, bit for bit

@@ -384,11 +384,11 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   P->pbatch = pbatch;
   // two output buffers + a side stream: a group's scatter (and its NVLink stores, when peers are set) overlaps the next
   // group's f! evaluations
-  // (one GPU: the scatter and the next f! compete for the same L2 / DRAM — measured on C4, r2: 14.06 ms overlapped vs
-  //  13.08 ms in sequence; with several ranks the scatter's NVLink stores are latency the next f! hides)
-  P->double_buffer = P->sp_kind == SP_CSC && P->strategy == 1 && P->world > 1 && (int64_t)P->local_colors.size() > slabs;
+  // Off by default since r2: the scatter and the next f! compete for the same L2 / DRAM, and the NVLink stores of a
+  // 5 MB colour need no hiding.  C4, ms per Jacobian, sequence vs overlapped: 13.08 / 14.06 (1 GPU), 7.06 / 7.24 (2),
+  // 3.65 / 3.72 (4), 2.08 / 2.17 (8).  FDB_FORCE_OVERLAP=1 switches the double-buffered side-stream form back on.
+  P->double_buffer = false;
   { const char *on = getenv("FDB_FORCE_OVERLAP"); if (on && on[0] == '1' && P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs) P->double_buffer = true; }
-  { const char *off = getenv("FDB_NO_OVERLAP"); if (off && off[0] == '1') P->double_buffer = false; }   // A/B switch (profiles/)
   const size_t nbuf = P->double_buffer ? 2 : 1;
   CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));

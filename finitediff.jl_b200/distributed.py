@@ -5,10 +5,10 @@ so there is NO collective on the data path until the end, where every rank needs
 Two implementations of that final exchange:
 
   "p2p"  (default on NVLink/NVSwitch)  the diff+scatter kernel itself stores every value it owns into rank 0's nzval
-         buffer (gather="root"; peer pointer from CUDA IPC, passed to the plan with fdb_plan_set_peers) — compute and
-         gather are one kernel, overlapped with the next colour's f! on a side stream; a stream-ordered NCCL all-reduce
-         of one flag word is the only barrier.  gather="all" adds one NCCL broadcast of nzval; gather="all_p2p" stores
-         to every peer from the kernel (fine up to 4 GPUs, pathological at 8 — see ShardedJacobian).
+         buffer (gather="root": rank 0's buffer is mapped by every rank over CUDA IPC and passed as THE J of plans created
+         with shared_j) — compute and gather are one kernel; the ranks are ordered by the C ABI's device-side barrier
+         (fdb_sync, DeviceBarrier below), no NCCL call per Jacobian.  gather="all" adds one NCCL broadcast of nzval;
+         gather="all_p2p" stores to every peer from the kernel (fine up to 4 GPUs, pathological at 8 — see ShardedJacobian).
   "nccl" (fallback; also what the CPU/gloo tests exercise)  each rank packs the entries it owns into a compact
          buffer, all_gather, then un-permutes into nzval.
 

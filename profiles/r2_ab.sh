@@ -1,6 +1,8 @@
 #!/bin/bash
 # round-2 A/B measurements (one GPU): staged vs gather scatter (C2 fwd/central), eps lists vs windows and overlap on/off (C4),
 # C5 alone; then ncu launch lists + full captures of the kernels bench.py reports on.  Run under gpurun from the repo root.
+# (record of the run as it was made: at that commit the side-stream overlap was ON for strategy 2 and FDB_NO_OVERLAP=1
+#  switched it off; since then the overlap is off by default and FDB_FORCE_OVERLAP=1 switches it on)
 set -u
 O=gpurun_out
 B="python bench.py --no-cpu --no-e2e --no-extras"

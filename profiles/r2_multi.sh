@@ -10,7 +10,7 @@ if [ "$N" = "2" ]; then
   tail -15 $O/r2_multi2_tests.log
 fi
 run c4            $TR bench.py --gpus $N --steps 20 --warmup 5
-run c4_nooverlap  FDB_NO_OVERLAP=1 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e
+run c4_overlap    FDB_FORCE_OVERLAP=1 $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e
 if [ "$N" != "8" ]; then
 run c4_ncclbar    $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e --barrier nccl
 run c4_onelaunch  $TR bench.py --gpus $N --steps 20 --warmup 5 --no-cpu --no-e2e --strategy 3

@@ -1,6 +1,8 @@
 #!/bin/bash
 # round-2 ncu evidence (one GPU, under gpurun): launch lists + full captures of every kernel bench.py reports a roofline
 # for.  Per-launch times are cold-cache and serialised: compare SHARES with bench.py's live numbers, not absolutes.
+# (record of the run as it was made: at that commit the side-stream overlap was ON for strategy 2 and FDB_NO_OVERLAP=1
+#  switched it off; since then the overlap is off by default and FDB_FORCE_OVERLAP=1 switches it on)
 set -u
 O=gpurun_out
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,lts__t_sector_hit_rate.pct"

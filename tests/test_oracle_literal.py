@@ -220,3 +220,30 @@ def test_oracle_cacheless_matches_literal_transcription(oracle, kind, seed):
     assert ro["fcalls"] == rl["fcalls"] == ((1 if fdtype == "forward" else 0) +
                                             (n if cv is None else int(cv.max())) * (1 if fdtype == "forward" else 2))
     assert np.array_equal(Jo, Jl, equal_nan=True), f"{kind} {fdtype} seed {seed}"
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("fdtype", ["forward", "central"])
+def test_oracle_dense_branch_with_colorvec_matches_literal(oracle, fdtype, seed):
+    """sparsity === nothing WITH a caller-supplied colorvec, as jacobians.jl:547-557 / :589-598 are written: the loop runs
+    color_i in 1:maximum(colorvec), perturbs component color_i, writes J[:, color_i]; no fill_matrix!, later columns keep
+    their contents (VERDICT r1 missing #6; the GPU path reproduces it through fdb_plan_create_dense_colorvec)."""
+    rng = np.random.default_rng(7000 + seed)
+    m, n = int(rng.integers(2, 9)), int(rng.integers(3, 10))
+    maxc = int(rng.integers(1, n + 1))
+    cv = rng.integers(1, maxc + 1, size=n).astype(np.int64)
+    cv[int(rng.integers(0, n))] = maxc
+    W = rng.normal(size=(m, n))
+
+    def f(fx, x):
+        fx[:] = np.sin(W @ x) + 0.5 * (W @ x) ** 2
+
+    x = rng.normal(size=n) + 1.5
+    Jl = np.full((m, n), -7.5)
+    cache_l = dict(x1=np.full(n, np.nan), x2=np.full(n, np.nan), fx=np.full(m, np.nan), fx1=np.full(m, np.nan))
+    rl = lit.finite_difference_jacobian(Jl, f, x.copy(), cache_l, None, fdtype=fdtype, colorvec=cv, sparsity=None)
+    Jo = np.full(m * n, -7.5)
+    ro = oracle.jacobian(oracle.Problem.dense(m, n), Jo, f, x.copy(), fdtype=FD[fdtype], colorvec=cv)
+    assert ro["fcalls"] == rl["fcalls"] == (maxc + 1 if fdtype == "forward" else 2 * maxc)
+    assert np.array_equal(Jo.reshape(m, n, order="F"), Jl)
+    assert (Jl[:, maxc:] == -7.5).all() and not (Jl[:, :maxc] == -7.5).any()
