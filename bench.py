@@ -479,10 +479,10 @@ def known_traffic(key):
         d = json.loads(p.read_text())
         v = d.get(key)
         if isinstance(v, dict):
-            return v.get("bytes"), v.get("source")
+            return v.get("bytes"), v.get("source"), bool(v.get("per_jacobian", False))
         if v is not None:
-            return v, "profiles/ (round-1 capture)"
-    return None, None
+            return v, "profiles/ (round-1 capture)", False
+    return None, None, False
 
 
 def traffic_key(workload, fdtype, info):
@@ -507,19 +507,21 @@ def scatter_kernel_name(info, fdtype):
 
 def roofline_record(info, fdtype, scat_ms, scat_n, tsteps, traffic_key):
     peak, peak_src = peaks()
-    per_jac = scat_ms / tsteps if tsteps else 0.0
+    per_jac_ms = scat_ms / tsteps if tsteps else 0.0
     launches = scat_n / tsteps if tsteps else 0
     moved = info["moved_bytes_scatter"]
     survey = info["alg_bytes_scatter"]
-    achieved = moved / (per_jac * 1e-3) / 1e9 if per_jac > 0 else None
-    traffic, tsrc = known_traffic(traffic_key)
+    achieved = moved / (per_jac_ms * 1e-3) / 1e9 if per_jac_ms > 0 else None
+    traffic, tsrc, per_jac = known_traffic(traffic_key)
+    traffic_per_jac = (traffic if per_jac else traffic * launches) if traffic else None
     return {"bound": "hbm", "kernel": scatter_kernel_name(info, fdtype), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
-            "bytes_per_launch": moved / launches if launches else None, "launch_ms": per_jac / launches if launches else None,
-            "bytes_per_jacobian": moved, "scatter_ms_per_jacobian": per_jac, "scatter_launches_per_jacobian": launches,
+            "bytes_per_launch": moved / launches if launches else None, "launch_ms": per_jac_ms / launches if launches else None,
+            "bytes_per_jacobian": moved, "scatter_ms_per_jacobian": per_jac_ms, "scatter_launches_per_jacobian": launches,
             "survey_bytes_per_jacobian": survey,
-            "achieved_vs_reference_shape": (survey / (per_jac * 1e-3) / 1e9 / peak) if per_jac > 0 else None,
-            "frac_traffic": (traffic * launches / (per_jac * 1e-3) / 1e9 / peak) if (traffic and per_jac > 0 and launches) else None,
+            "achieved_vs_reference_shape": (survey / (per_jac_ms * 1e-3) / 1e9 / peak) if per_jac_ms > 0 else None,
+            "traffic_per_jacobian": traffic_per_jac,
+            "frac_traffic": (traffic_per_jac / (per_jac_ms * 1e-3) / 1e9 / peak) if (traffic_per_jac and per_jac_ms > 0) else None,
             "note": "achieved = compulsory bytes of the shipped formulation (fdb_plan_info.moved_bytes_scatter: int32 rows, narrow "
                     "colours / slots, each slab value and J slot once, fx once) / CUDA-event time of the scatter launches; "
                     "achieved_vs_reference_shape uses SURVEY.md §8(d)'s reference-shaped count (Int64 indices, fx re-read per "

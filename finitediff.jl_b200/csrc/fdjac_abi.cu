@@ -139,6 +139,7 @@ struct fdb_plan {
   int32_t *cm_row = nullptr;
   void *cm_slot = nullptr;            // int32 (nzval slot) or int64 (explicit destination: dest != nullptr)
   int64_t *cm_start = nullptr;        // device [n_local + 1]
+  double *fx_cm = nullptr;            // forward: f(x) in colour-major order (rebuilt by every Jacobian)
   std::vector<int64_t> cm_start_h;    // host copy; [n_local] .. cm_invalid_end = entries of columns without a valid colour
   int64_t cm_invalid_end = 0;
   // TMA-staged form of the fused pass (row-local patterns; kernels_staged.cuh)
@@ -511,6 +512,10 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   TRY(P->alloc_t(&P->cm_start, (size_t)n_local + 1));
   CU(cudaMemcpy(P->cm_start, P->cm_start_h.data(), ((size_t)n_local + 1) * 8, cudaMemcpyHostToDevice));
   TRY(P->alloc_t(&P->cm_row, (size_t)std::max<int64_t>(e_local, 1)));
+  {
+    const char *off = getenv("FDB_NO_FX_CM");
+    if (P->fdtype == FDB_FORWARD && e_local > 0 && !(off && off[0] == '1')) TRY(P->alloc_t(&P->fx_cm, (size_t)e_local));
+  }
   const bool wide = P->dest != nullptr;
   TRY(P->alloc(&P->cm_slot, (size_t)std::max<int64_t>(e_local, 1) * (wide ? 8 : 4)));
   if (ncols == 0 || e_local == 0) return FDB_OK;
@@ -1047,7 +1052,7 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
     if (P->sp_kind == SP_CSC || P->sp_kind == SP_COO) {
       if (P->sp_kind == SP_CSC && P->strategy == 1) {
         const int64_t e_local = P->cm_start_h.empty() ? 0 : P->cm_start_h.back();
-        info->moved_bytes_scatter = e_local * (4 + (P->dest ? 8 : 4) + 8 * slabs_read + 8) + fx_once;
+        info->moved_bytes_scatter = e_local * (4 + (P->dest ? 8 : 4) + 8 * slabs_read + 8) + fx_once + (P->fx_cm ? e_local * (4 + 8 + 8) : 0);
       } else {
         const int64_t C = std::max<int32_t>(P->C, 1);
         const int64_t owned = P->world > 1 ? P->E * (int64_t)P->local_colors.size() / C : P->E;   // approx. share
@@ -1282,6 +1287,16 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     else { TRY(call_f(P, f, ctx, fx, x, 1, s)); vfx = fx; } // :541-542
   }
   if (eps_beside_fx) CU(cudaStreamWaitEvent(s, P->ev_eps, 0));
+  // colour-major lists, forward: f(x) once into list order (read as a coalesced stream by every colour's launch)
+  if (MODE == kForward && P->sp_kind == SP_CSC && P->strategy == 1 && P->fx_cm && n_local > 0) {
+    const int64_t cnt = P->cm_start_h[(size_t)n_local];
+    if (cnt > 0) {
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((cnt + kThreads * 4 - 1) / (kThreads * 4), (int64_t)P->sm_count * 16));
+      ScatterTimer tm(P, s);            // part of the diff+scatter formulation: timed with it
+      gather_fx_cm<<<grid, kThreads, 0, s>>>(P->cm_row, vfx, cnt, P->fx_cm);
+      P->cnt.kernel_launches += 1;
+    }
+  }
   // build the perturbed points of local colours [li0, li0+kc) into the point buffers (one pass over x per 4 colours)
   auto perturb_window = [&](int64_t li0, int64_t kc) -> fdb_status {
       for (int64_t q0 = 0; q0 < kc; q0 += kPerturbMaxPoints) {
@@ -1336,6 +1351,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     CmArgs a{};
     a.row = P->cm_row; a.slot = P->cm_slot; a.seg_start = P->cm_start; a.local_colors = P->d_local_colors;
     a.fx = vfx; a.Fp = Fp_g; a.Fm = Fm_g; a.eps = P->eps; a.J = J; a.peers = P->d_peers; a.n_peers = P->n_peers;
+    a.fx_cm = MODE == kForward ? P->fx_cm : nullptr;
     a.l0 = (int32_t)l0; a.G = (int32_t)G; a.ldF = sF;
     a.m = COMPLEX ? 2 * P->m : P->m;
     // (software L2 prefetch of the next colour's slab: measured SLOWER on C4 — 1.255 vs 0.962 ms — the 40 MB slab, the next

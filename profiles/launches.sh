@@ -2,7 +2,7 @@
 # ncu launch list (device time per launch, cold-cache + serialised: compare SHARES) of one bench configuration.
 # Usage: bash profiles/launches.sh <tag> <bench args...>    -> gpurun_out/<tag>.csv
 TAG=$1; shift
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fdb|k_tridiag|k_ellrows|k_lap5|k_rank1|k_block_sums|DeviceRadixSort|DeviceScan" -c 600 --csv --log-file gpurun_out/${TAG}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"diff_|perturb_|color_sumsq|finalize_eps|gather_fx|zero_slots|replicate_x|set_components|component_eps|k_tridiag|k_ellrows|k_lap5|k_rank1|k_block_sums" -c 600 --csv --log-file gpurun_out/${TAG}.csv \
     python bench.py "$@" --steps 2 --warmup 3 --no-cpu --no-e2e --no-graph --spin 0 > gpurun_out/${TAG}.log 2>&1
 python - "$TAG" <<'PY'
 import csv, collections, sys
