@@ -514,7 +514,12 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   TRY(P->alloc_t(&P->cm_row, (size_t)std::max<int64_t>(e_local, 1)));
   {
     const char *off = getenv("FDB_NO_FX_CM");
-    if (P->fdtype == FDB_FORWARD && e_local > 0 && !(off && off[0] == '1')) TRY(P->alloc_t(&P->fx_cm, (size_t)e_local));
+    // only where f(x) would otherwise be dragged through DRAM once per launch: several launches per Jacobian (colours
+    // sharded over GPUs, or more colours than resident slabs).  r2 A/B on C4, scatter ms per Jacobian: 64 per-colour launches
+    // 1.56 -> 1.35; one launch over all colours 1.23 -> 1.22 (+ 320 MB): not used there.
+    const char *force = getenv("FDB_FORCE_FX_CM");
+    const bool want = P->n_groups > 1 || (force && force[0] == '1');
+    if (P->fdtype == FDB_FORWARD && e_local > 0 && want && !(off && off[0] == '1')) TRY(P->alloc_t(&P->fx_cm, (size_t)e_local));
   }
   const bool wide = P->dest != nullptr;
   TRY(P->alloc(&P->cm_slot, (size_t)std::max<int64_t>(e_local, 1) * (wide ? 8 : 4)));

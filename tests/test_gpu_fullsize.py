@@ -116,8 +116,10 @@ def test_c3_full_size_sampled_columns_bitexact(pkg, oracle, dev, fdtype):
 
 
 # ---------------------------------------------------------------------------------------------------- C4 full size
-@pytest.mark.parametrize("strategy", [1, 2])
+@pytest.mark.parametrize("strategy", [0, 1, 2, 3])
 def test_c4_full_size_bitexact(pkg, oracle, dev, strategy):
+    """strategy 0 = auto (random pattern, one GPU: colour-major lists with every slab resident, f(x) pre-gathered into list
+    order), 1 = storage-order pass, 2 = colour-major lists per group, 3 = colour-major lists, one launch"""
     import bench
     fdtype = "forward"
     prob = bench.build_gpu_problem(pkg, "c4", fdtype, dev, 0, 1, 1, use_graph=False, strategy=strategy)
@@ -125,7 +127,9 @@ def test_c4_full_size_bitexact(pkg, oracle, dev, strategy):
     pkg.finite_difference_jacobian_(J, f, x, cache)
     torch.cuda.synchronize()
     plan = cache._last_plan
-    assert plan.info()["strategy"] == strategy - 1
+    info = plan.info()
+    assert info["strategy"] == (1 if strategy in (0, 2, 3) else 0)
+    assert info["lists_resident"] == (1 if strategy in (0, 3) else 0) and info["n_groups"] == (64 if strategy == 2 else 1)
     eps = plan.eps()
     n, K = prob["n"], 8
     d_cols, d_coef, cv_t = prob["keep"]
