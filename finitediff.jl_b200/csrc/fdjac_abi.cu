@@ -130,6 +130,14 @@ struct fdb_plan {
   int strategy = 0;
   bool strategy_auto = true;
   bool lists_resident = false;         // strategy 1 with every local colour's f! output resident: ONE launch over the lists
+  // A/B switches (environment, read ONCE when the plan is created — never on the hot path)
+  struct Tunables {
+    bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
+    bool no_fx_cm = false, force_fx_cm = false;
+    int hi_stream = -1;                // -1: by pattern (random => evict-first slab gathers), 0 / 1: forced
+    int stages = 2;
+    char staged_variant[3] = {'6', 'n', 0};
+  } tune;
   bool double_buffer = false;          // two output buffers so a group's scatter overlaps the next group's f!
   cudaStream_t side = nullptr;
   cudaEvent_t ev_f[2] = {nullptr, nullptr}, ev_scat[2] = {nullptr, nullptr};
@@ -389,7 +397,7 @@ static fdb_status finish_colored_plan(fdb_plan *P, const fdb_plan_opts *o, const
   // 5 MB colour need no hiding.  C4, ms per Jacobian, sequence vs overlapped: 13.08 / 14.06 (1 GPU), 7.06 / 7.24 (2),
   // 3.65 / 3.72 (4), 2.08 / 2.17 (8).  FDB_FORCE_OVERLAP=1 switches the double-buffered side-stream form back on.
   P->double_buffer = false;
-  { const char *on = getenv("FDB_FORCE_OVERLAP"); if (on && on[0] == '1' && P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs) P->double_buffer = true; }
+  if (P->tune.force_overlap && P->sp_kind == SP_CSC && P->strategy == 1 && (int64_t)P->local_colors.size() > slabs) P->double_buffer = true;
   const size_t nbuf = P->double_buffer ? 2 : 1;
   CU(cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
@@ -513,13 +521,11 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   CU(cudaMemcpy(P->cm_start, P->cm_start_h.data(), ((size_t)n_local + 1) * 8, cudaMemcpyHostToDevice));
   TRY(P->alloc_t(&P->cm_row, (size_t)std::max<int64_t>(e_local, 1)));
   {
-    const char *off = getenv("FDB_NO_FX_CM");
     // only where f(x) would otherwise be dragged through DRAM once per launch: several launches per Jacobian (colours
     // sharded over GPUs, or more colours than resident slabs).  r2 A/B on C4, scatter ms per Jacobian: 64 per-colour launches
     // 1.56 -> 1.35; one launch over all colours 1.23 -> 1.22 (+ 320 MB): not used there.
-    const char *force = getenv("FDB_FORCE_FX_CM");
-    const bool want = P->n_groups > 1 || (force && force[0] == '1');
-    if (P->fdtype == FDB_FORWARD && e_local > 0 && want && !(off && off[0] == '1')) TRY(P->alloc_t(&P->fx_cm, (size_t)e_local));
+    const bool want = P->n_groups > 1 || P->tune.force_fx_cm;
+    if (P->fdtype == FDB_FORWARD && e_local > 0 && want && !P->tune.no_fx_cm) TRY(P->alloc_t(&P->fx_cm, (size_t)e_local));
   }
   const bool wide = P->dest != nullptr;
   TRY(P->alloc(&P->cm_slot, (size_t)std::max<int64_t>(e_local, 1) * (wide ? 8 : 4)));
@@ -566,16 +572,11 @@ static fdb_status build_cm_lists(fdb_plan *P, const std::vector<unsigned long lo
   return FDB_OK;
 }
 
-// r2 A/B on C2 (same box, 1965 MHz, scatter us forward / central): gather form 123.4 / 139.5; staged 8 blocks 112.5 / 137.5;
-// 6 blocks + index prefetch 108.0 / 139.0; 6 blocks, no prefetch 105.6 / 130.6 (kept)
-static const char kStagedDefaultVariant[3] = "6n";
-
 // TMA-staged fused pass: eligible when the whole Jacobian is one resident group on one rank, the destination is the
 // identity (CSC nzval) and every 1024-entry tile touches a short row window (row-local pattern).
 static fdb_status try_stage_plan(fdb_plan *P) {
   P->staged = false;
-  const char *off = getenv("FDB_NO_STAGED");
-  if (off && off[0] == '1') return FDB_OK;
+  if (P->tune.no_staged) return FDB_OK;
   if (P->sp_kind != SP_CSC || P->dest != nullptr || P->strategy != 0 || P->world != 1 || P->n_groups != 1) return FDB_OK;
   if (P->fdtype == FDB_COMPLEX || P->C < 1) return FDB_OK;
   const int nwin = P->fdtype == FDB_CENTRAL ? 2 * P->C : P->C + 1;
@@ -606,6 +607,29 @@ static fdb_status read_plan_err(uint32_t *d_err, const char *what) {
   return FDB_OK;
 }
 
+static bool env_is(const char *name, char c) {
+  const char *v = getenv(name);
+  return v && v[0] == c;
+}
+
+// r2 A/B on C2 (same box, 1965 MHz, scatter us forward / central): gather form 123.4 / 139.5; staged 8 blocks 112.5 / 137.5;
+// 6 blocks + index prefetch 108.0 / 139.0; 6 blocks, no prefetch 105.6 / 130.6 (default "6n"); 5 / 4 blocks 106.5 / 108.6
+static void read_tunables(fdb_plan *P) {
+  auto &t = P->tune;
+  t.no_staged = env_is("FDB_NO_STAGED", '1');
+  t.no_eps_lists = env_is("FDB_NO_EPS_LISTS", '1');
+  t.no_eps_overlap = env_is("FDB_NO_EPS_OVERLAP", '1');
+  t.cm_prefetch = env_is("FDB_CM_PREFETCH", '1');
+  t.force_overlap = env_is("FDB_FORCE_OVERLAP", '1');
+  t.no_fx_cm = env_is("FDB_NO_FX_CM", '1');
+  t.force_fx_cm = env_is("FDB_FORCE_FX_CM", '1');
+  if (const char *hs = getenv("FDB_HI_STREAM")) t.hi_stream = hs[0] == '1' ? 1 : 0;
+  if (env_is("FDB_STAGES", '3')) t.stages = 3;
+  if (const char *v = getenv("FDB_STAGED_VARIANT")) {
+    if (v[0]) { t.staged_variant[0] = v[0]; t.staged_variant[1] = v[1] ? v[1] : 'n'; }
+  }
+}
+
 static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, int64_t n) {
   if (!out) return fail(FDB_ERR_INVALID, "plan output pointer is NULL");
   *out = nullptr;
@@ -624,6 +648,7 @@ static fdb_status new_plan(fdb_plan **out, const fdb_plan_opts *o, int64_t m, in
   P->no_drift = o ? o->no_drift : 0;
   P->use_graph = o && o->use_graph != 0;
   P->shared_J = o && o->shared_j != 0;
+  read_tunables(P);
   P->world = (o && o->world > 1) ? o->world : 1;
   P->rank = (o && o->world > 1) ? o->rank : 0;
   if (P->rank < 0 || P->rank >= P->world) {
@@ -1216,8 +1241,7 @@ static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double a
   }
   EpsParams prm{P->fdtype == FDB_CENTRAL ? 1 : 0, relstep, absstep, dir};
   if (P->eps_lists) {
-    const char *off = getenv("FDB_NO_EPS_LISTS");
-    if (!(off && off[0] == '1')) {
+    if (!P->tune.no_eps_lists) {
       dim3 grid((unsigned)std::min<int64_t>(P->eps_list_max_chunks, 1024), (unsigned)std::min<int32_t>(C, 65535));
       color_sumsq_lists<<<grid, kThreads, 0, s>>>(x, P->cols_by_color, P->bucket_start_d, P->chunk_base_d, C, P->eps_list_partial);
       finalize_eps_lists<<<(int)std::min<int64_t>(((int64_t)C * 32 + kThreads - 1) / kThreads, (int64_t)P->sm_count * 8), kThreads, 0, s>>>(
@@ -1274,7 +1298,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
   // forward mode without f_in: f(x) (jacobians.jl:541) and the step-size pass are independent — the eps kernels run on the
   // side stream beside the user's f(x) and are joined before the first perturbation (a parallel branch of the CUDA graph)
   bool eps_beside_fx = MODE == kForward && !f_in && !P->ext_eps && P->side && P->ev_fork && P->C > 0;
-  { const char *off = getenv("FDB_NO_EPS_OVERLAP"); if (off && off[0] == '1') eps_beside_fx = false; }
+  if (P->tune.no_eps_overlap) eps_beside_fx = false;
   if (P->ext_eps) {
     // sharded runs: the step sizes of the FULL x come from outside (fdb_color_eps on the full vector)
     if (P->C > 0) CU(cudaMemcpyAsync(P->eps, P->ext_eps, (size_t)P->C * 8, cudaMemcpyDeviceToDevice, s));
@@ -1361,7 +1385,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     a.m = COMPLEX ? 2 * P->m : P->m;
     // (software L2 prefetch of the next colour's slab: measured SLOWER on C4 — 1.255 vs 0.962 ms — the 40 MB slab, the next
     //  one and f(x) do not fit the L2 together; off unless FDB_CM_PREFETCH=1)
-    { const char *pf = getenv("FDB_CM_PREFETCH"); a.prefetch_next = (G > 1 && pf && pf[0] == '1') ? 1 : 0; }
+    a.prefetch_next = (G > 1 && P->tune.cm_prefetch) ? 1 : 0;
     const int64_t tiles = (total + kCmTile - 1) / kCmTile;
     ScatterTimer tm(P, ss);
     if (wide) {
@@ -1446,8 +1470,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
       a.j_aligned = (reinterpret_cast<uintptr_t>(J) & 15) == 0 && P->peers_aligned;
       {
         // random patterns (mean row jump beyond a few cache lines): slab gathers are read-once
-        const char *hs = getenv("FDB_HI_STREAM");
-        a.hi_stream = hs ? (hs[0] == '1') : (P->mean_row_jump > 4096.0);
+        a.hi_stream = P->tune.hi_stream >= 0 ? P->tune.hi_stream : (P->mean_row_jump > 4096.0 ? 1 : 0);
       }
       const size_t sm = P->C <= kSmemTable ? (size_t)P->C * (sizeof(double) + sizeof(int32_t)) : 0;
       ScatterTimer tm(P, s);
@@ -1466,14 +1489,12 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             sa.fx = vfx; sa.Fp = P->Fp; sa.Fm = P->Fm; sa.eps = P->eps; sa.J = J; sa.C = P->C; sa.W = P->stage_W;
             sa.ldF = sF; sa.src_len = P->ldF; sa.E = P->E; sa.j_aligned = a.j_aligned;
             const int nwin = CENTRAL ? 2 * P->C : P->C + 1;
-            const char *st_env = getenv("FDB_STAGES");
-            int stages = st_env && st_env[0] == '3' ? 3 : 2;
+            int stages = P->tune.stages;
             if ((size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;
             sa.stages = stages;
             const size_t ssm = (size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
             // variants (profiles/ A/B; FDB_STAGED_VARIANT = 8n | 6p | 6n): resident blocks per SM x index prefetch
-            const char *v_env = getenv("FDB_STAGED_VARIANT");
-            const char v0 = v_env ? v_env[0] : kStagedDefaultVariant[0], v1 = v_env && v_env[0] ? v_env[1] : kStagedDefaultVariant[1];
+            const char v0 = P->tune.staged_variant[0], v1 = P->tune.staged_variant[1];
             auto go = [&](auto kern) {
               const int grid = resident_grid(P, kern, ssm, tiles);
               kern<<<grid, kThreads, ssm, s>>>(sa);
