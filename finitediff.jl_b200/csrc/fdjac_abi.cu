@@ -1500,8 +1500,6 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
               kern<<<grid, kThreads, ssm, s>>>(sa);
             };
             if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false>);
-            else if (v0 == '5') go(diff_scatter_staged<CT, MODE, 5, false>);
-            else if (v0 == '4') go(diff_scatter_staged<CT, MODE, 4, false>);
             else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false>);
             else go(diff_scatter_staged<CT, MODE, 6, true>);
           }
