@@ -628,6 +628,8 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
         return gpu_arm_multi(args, pkg, dev, rank, world)
     workload, fdtype = args.workload, args.fdtype
+    if args.group > 1:
+        return gpu_arm_group(args, pkg, dev)
     rec, prob, plan, nnz = run_single(pkg, workload, fdtype, dev, args, args.steps, spin_s=args.spin, strategy=args.strategy,
                                       sample_clocks=True)
     clk = rec.pop("clocks")
@@ -716,6 +718,61 @@ def gpu_arm(args):
         "clocks": clk, "workloads": others,
     }
     print(json.dumps(line))
+
+
+def gpu_arm_group(args, pkg, dev):
+    """`--group N`: ONE process drives N GPUs through the C ABI's fdb_group_* (what a Julia host calling
+    finite_difference_jacobian! once would use) — no torch.distributed, no NCCL, no second process.  C4, colours sharded over
+    the devices, every member's scatter stores straight into device 0's nzval; bit-compared with the 1-GPU Jacobian."""
+    import torch
+    from finitediff_jl_b200 import distributed as fdist
+    L = pkg._lib
+    n_dev = args.group
+    if torch.cuda.device_count() < n_dev:
+        raise SystemExit(f"--group {n_dev} needs {n_dev} visible GPUs")
+    fdtype = args.fdtype
+    r1, p1, pl1, nnz = run_single(pkg, "c4", fdtype, dev, args, max(5, min(args.steps, 20)))
+    J1, eps1 = p1["J"].nzval.clone(), pl1.eps().copy()
+    J, x, cv = p1["J"], p1["x"], p1["keep"][2]
+    d_cols, d_coef = p1["keep"][0], p1["keep"][1]
+    devices = list(range(n_dev))
+    keep, fs = [], []
+    for d in devices:
+        dd = torch.device("cuda", d)
+        c_d, a_d = (d_cols, d_coef) if d == dev.index else (d_cols.to(dd), d_coef.to(dd))
+        ctx = L.EllCtx(p1["n"], C4_K, c_d.data_ptr(), a_d.data_ptr(), 0)
+        keep.append((c_d, a_d, ctx))
+        fs.append(pkg.NativeFn(C.cast(L.synth().fdbs_ellrows, C.c_void_p).value, ctx))
+    del pl1
+    J.nzval.fill_(float("nan"))
+    g = fdist.GroupJacobian(J, cv, fdtype, devices, use_graph=args.graph)
+
+    def step():
+        g.run(fs, x)
+
+    step()
+    g.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    g.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()          # the root stream waits on every member's completion event inside fdb_group_jacobian
+    g.synchronize()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    equal = bool(torch.equal(J.nzval, J1))
+    line = {"metric": "jacobian_nnz_per_s", "value": nnz / (ms_step * 1e-3), "unit": "nnz/s", "n_gpus": n_dev, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config("c4", fdtype),
+            "details": {"driver": "one process, fdb_group_create_csc / fdb_group_jacobian (C ABI), CUDA graph per member" if args.graph else "one process, fdb_group_*",
+                        "devices": devices},
+            "strong_scaling": {"t1_ms": r1["ms_per_step"], "tN_ms": ms_step, "speedup": r1["ms_per_step"] / ms_step, "n_gpus": n_dev},
+            "parity": {"sharded_equals_unsharded": {"equal": equal, "eps_equal": bool(np.array_equal(g.plans[0].eps(), eps1))}, "ok": equal},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": None}
+    print(json.dumps(line))
+    g.close()
 
 
 def gpu_arm_multi(args, pkg, dev, rank, world):
@@ -942,6 +999,8 @@ def main():
     ap.add_argument("--shard", default="colors", choices=["colors", "columns"],
                     help="N>1: colour set (c4) or contiguous column blocks with a slice-aware f! (c2)")
     ap.add_argument("--spin", type=float, default=0.6, help="seconds of extra warm-up of the same step (lets the 100 ms clock sampler see the load; 0 under ncu)")
+    ap.add_argument("--group", type=int, default=1,
+                    help="run C4 over N GPUs from ONE process through fdb_group_* (no torchrun); ad-hoc, not the driver contract")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
@@ -959,6 +1018,9 @@ def main():
         args.extras = False
     if args.fdtype == "complex" and args.workload not in ("c1", "c2"):
         raise SystemExit("--fdtype complex is benchmarked on the tridiagonal workloads (c1, c2)")
+    if args.group > 1:
+        args.workload, args.extras = "c4", False
+        args.fdtype = args.fdtype or "forward"
     if args.steps is None:
         args.steps = 5 if args.impl == "reference" else {"c1": 500, "c2": 200, "c3": 50, "c4": 30, "c5": 5}[args.workload]
     if args.impl == "reference":

@@ -110,11 +110,9 @@ static fdb_status group_create(fdb_group **out, int n_devices, const int *device
     o.rank = i;
     o.world = n_devices;
     o.shared_j = n_devices > 1 ? 1 : 0;
-    fdb_status st = make(i, &o, &g->plans[i]);
-    if (st != FDB_OK) { free_group(g); return st; }
-    if (i == 0) continue;
-    DeviceGuard dg(devices[i]);
-    if (devices[i] != root) {
+    // peer access to the root FIRST: the member's plan build may already read index arrays that live on the root device
+    if (i > 0 && devices[i] != root) {
+      DeviceGuard dgp(devices[i]);
       int can = 0;
       cudaDeviceCanAccessPeer(&can, devices[i], root);
       if (!can) { free_group(g); return fail(FDB_ERR_UNSUPPORTED, "device %d cannot access device %d (no peer path)", devices[i], root); }
@@ -125,6 +123,10 @@ static fdb_status group_create(fdb_group **out, int n_devices, const int *device
       }
       cudaGetLastError();
     }
+    fdb_status st = make(i, &o, &g->plans[i]);
+    if (st != FDB_OK) { free_group(g); return st; }
+    if (i == 0) continue;
+    DeviceGuard dg(devices[i]);
     cudaError_t e = cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { free_group(g); return fail(FDB_ERR_CUDA, "group stream/event: %s", cudaGetErrorString(e)); }
