@@ -133,7 +133,7 @@ struct fdb_plan {
   // A/B switches (environment, read ONCE when the plan is created — never on the hot path)
   struct Tunables {
     bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
-    bool no_fx_cm = false, force_fx_cm = false;
+    bool no_fx_cm = false, force_fx_cm = false, no_pack = false;
     int hi_stream = -1;                // -1: by pattern (random => evict-first slab gathers), 0 / 1: forced
     int stages = 2;
     char staged_variant[3] = {'6', 'n', 0};
@@ -154,7 +154,7 @@ struct fdb_plan {
   uint16_t *row16 = nullptr;
   int32_t *tile_w0 = nullptr;
   int32_t stage_W = 0;
-  bool staged = false;
+  bool staged = false, stage_packed = false;
   std::vector<int64_t> bucket_start;   // [C+2] offsets into cols_by_color; bucket C = columns without a valid colour
   int lanes = 1;
   double mean_row_jump = 0.0;
@@ -587,10 +587,22 @@ static fdb_status try_stage_plan(fdb_plan *P) {
   CU(cudaMemset(d_span, 0, 4));
   TRY(P->alloc_t(&P->tile_w0, (size_t)ntiles));
   TRY(P->alloc_t(&P->row16, (size_t)ntiles * kTile));
-  stage_prepare<<<(int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16), kThreads>>>(P->row32, ntiles, P->tile_w0, P->row16, d_span);
+  const int pgrid = (int)std::min<int64_t>(ntiles, (int64_t)P->sm_count * 16);
+  stage_prepare<uint8_t><<<pgrid, kThreads>>>(P->row32, ntiles, P->tile_w0, P->row16, d_span, nullptr, P->C);
   unsigned int span = 0;
   CU(cudaMemcpy(&span, d_span, 4, cudaMemcpyDeviceToHost));
   const int64_t W = ((int64_t)span + 1) & ~(int64_t)1;
+  // few colours, short windows: pack the entry's colour into the top 4 bits of its row offset (no colour stream at all)
+  P->stage_packed = P->C <= 14 && W <= 4096 && span > 0 && !P->tune.no_pack;
+  if (P->stage_packed) {
+    TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
+      using CT = decltype(tag);
+      stage_prepare<CT><<<pgrid, kThreads>>>(P->row32, ntiles, P->tile_w0, P->row16, d_span, (const CT *)P->ecolor, P->C);
+      CU(cudaGetLastError());
+      return FDB_OK;
+    }));
+    CU(cudaDeviceSynchronize());
+  }
   const size_t smem = (size_t)2 * nwin * W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
   if (span == 0 || span > 65535 || smem > (size_t)kStageMaxSmem) return FDB_OK;   // not row-local enough: keep the gather form
   P->stage_W = (int32_t)W;
@@ -623,6 +635,7 @@ static void read_tunables(fdb_plan *P) {
   t.force_overlap = env_is("FDB_FORCE_OVERLAP", '1');
   t.no_fx_cm = env_is("FDB_NO_FX_CM", '1');
   t.force_fx_cm = env_is("FDB_FORCE_FX_CM", '1');
+  t.no_pack = env_is("FDB_NO_PACK", '1');
   if (const char *hs = getenv("FDB_HI_STREAM")) t.hi_stream = hs[0] == '1' ? 1 : 0;
   if (env_is("FDB_STAGES", '3')) t.stages = 3;
   if (const char *v = getenv("FDB_STAGED_VARIANT")) {
@@ -1088,7 +1101,7 @@ fdb_status fdb_plan_info(const fdb_plan *P, fdb_plan_info_t *info) {
         const int64_t owned = P->world > 1 ? P->E * (int64_t)P->local_colors.size() / C : P->E;   // approx. share
         info->moved_bytes_scatter = P->E * (4 + ct) * std::max<int64_t>(P->n_groups, 1) + owned * (8 * slabs_read + 8 + (P->dest ? 8 : 0)) + fx_once;
         if (P->staged)   // 16-bit row offsets; every slab row and f(x) row staged once
-          info->moved_bytes_scatter = P->E * (2 + ct + 8) + 8 * P->m * (int64_t)(P->fdtype == FDB_CENTRAL ? 2 * P->C : P->C + 1);
+          info->moved_bytes_scatter = P->E * (2 + (P->stage_packed ? 0 : ct) + 8) + 8 * P->m * (int64_t)(P->fdtype == FDB_CENTRAL ? 2 * P->C : P->C + 1);
       }
     } else {
       info->moved_bytes_scatter = P->alg_bytes;
@@ -1499,9 +1512,10 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
               const int grid = resident_grid(P, kern, ssm, tiles);
               kern<<<grid, kThreads, ssm, s>>>(sa);
             };
-            if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false>);
-            else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false>);
-            else go(diff_scatter_staged<CT, MODE, 6, true>);
+            if (P->stage_packed) go(diff_scatter_staged<CT, MODE, 6, false, true>);
+            else if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false, false>);
+            else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false, false>);
+            else go(diff_scatter_staged<CT, MODE, 6, true, false>);
           }
         } else if (full) {
           const int grid = resident_grid(P, diff_scatter_ident<CT, MODE, true, kScatterMinBlocks>, sm, tiles);

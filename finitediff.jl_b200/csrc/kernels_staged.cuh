@@ -64,9 +64,11 @@ struct StagedArgs {
 };
 
 // plan time: window start (even) of every full tile, 16-bit offsets, largest span
+template <typename CT>
 __global__ void __launch_bounds__(kThreads)
 stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__restrict__ tile_w0, uint16_t *__restrict__ row16,
-              unsigned int *__restrict__ max_span) {
+              unsigned int *__restrict__ max_span, const CT *__restrict__ ecolor /* non-null: pack the colour into bits 12..15 */,
+              int32_t C) {
   __shared__ int32_t s_min[kThreads / 32], s_max[kThreads / 32];
   __shared__ int32_t s_w0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -98,8 +100,14 @@ stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__rest
     const int32_t w0 = s_w0;
 #pragma unroll
     for (int u = 0; u < kTile / kThreads; ++u) {
-      const int32_t d = r[u] - w0;
-      row16[tile * kTile + u * kThreads + threadIdx.x] = (uint16_t)(d > 65535 ? 65535 : d);
+      int32_t d = r[u] - w0;
+      d = d > 65535 ? 65535 : d;
+      if (ecolor) {                                      // packed form: offset < 4096 in bits 0..11, colour (15 = none) above
+        uint32_t k = (uint32_t)ecolor[tile * kTile + u * kThreads + threadIdx.x];
+        if (k >= (uint32_t)C) k = 15u;
+        d = (d & 0xFFF) | (int32_t)(k << 12);
+      }
+      row16[tile * kTile + u * kThreads + threadIdx.x] = (uint16_t)d;
     }
     __syncthreads();
   }
@@ -107,7 +115,9 @@ stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__rest
 
 // MINB: resident blocks per SM the register budget is cut for (8 -> 32 registers, 6 -> 40: no spill of the prefetched
 // index registers; with TMA doing the wide loads the kernel needs fewer resident warps than the gather form)
-template <typename CT, int MODE, int MINB, bool PREFETCH>
+// PACKED: few colours and short windows (C <= 14, W <= 4096): the entry's colour rides in the top 4 bits of its 16-bit row
+// offset — the per-entry colour stream is not read at all (2 index bytes per entry instead of 2 + |colour|)
+template <typename CT, int MODE, int MINB, bool PREFETCH, bool PACKED>
 __global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_staged(const StagedArgs a) {
   static_assert(MODE == kForward || MODE == kCentral, "staged scatter: forward / central");
@@ -171,8 +181,13 @@ diff_scatter_staged(const StagedArgs a) {
     const CT *__restrict__ ct = ecolor + tile * kTile;
     x.ra = __ldcs(reinterpret_cast<const ushort2 *>(rt + tid2));
     x.rb = __ldcs(reinterpret_cast<const ushort2 *>(rt + kHalf + tid2));
-    ld_color_pair<CT>(ct + tid2, x.ka0, x.ka1);
-    ld_color_pair<CT>(ct + kHalf + tid2, x.kb0, x.kb1);
+    if (PACKED) {
+      x.ka0 = x.ra.x >> 12; x.ka1 = x.ra.y >> 12; x.kb0 = x.rb.x >> 12; x.kb1 = x.rb.y >> 12;
+      x.ra.x &= 0xFFF; x.ra.y &= 0xFFF; x.rb.x &= 0xFFF; x.rb.y &= 0xFFF;
+    } else {
+      ld_color_pair<CT>(ct + tid2, x.ka0, x.ka1);
+      ld_color_pair<CT>(ct + kHalf + tid2, x.kb0, x.kb1);
+    }
     return x;
   };
   uint32_t it = 0;
