@@ -603,7 +603,7 @@ static fdb_status try_stage_plan(fdb_plan *P) {
     }));
     CU(cudaDeviceSynchronize());
   }
-  const size_t smem = (size_t)2 * nwin * W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
+  const size_t smem = (size_t)2 * nwin * W * 8 + 2 * kStagesMax * 8 + (size_t)P->C * 8;
   if (span == 0 || span > 65535 || smem > (size_t)kStageMaxSmem) return FDB_OK;   // not row-local enough: keep the gather form
   P->stage_W = (int32_t)W;
   P->staged = true;
@@ -1503,16 +1503,17 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             sa.ldF = sF; sa.src_len = P->ldF; sa.E = P->E; sa.j_aligned = a.j_aligned;
             const int nwin = CENTRAL ? 2 * P->C : P->C + 1;
             int stages = P->tune.stages;
-            if ((size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;
+            if ((size_t)stages * nwin * P->stage_W * 8 + 2 * kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;
             sa.stages = stages;
-            const size_t ssm = (size_t)stages * nwin * P->stage_W * 8 + kStagesMax * 8 + (size_t)P->C * 8;
+            const size_t ssm = (size_t)stages * nwin * P->stage_W * 8 + 2 * kStagesMax * 8 + (size_t)P->C * 8;
             // variants (profiles/ A/B; FDB_STAGED_VARIANT = 8n | 6p | 6n): resident blocks per SM x index prefetch
             const char v0 = P->tune.staged_variant[0], v1 = P->tune.staged_variant[1];
             auto go = [&](auto kern) {
               const int grid = resident_grid(P, kern, ssm, tiles);
               kern<<<grid, kThreads, ssm, s>>>(sa);
             };
-            if (P->stage_packed) go(diff_scatter_staged<CT, MODE, 6, false, true>);
+            if (P->stage_packed && v1 == 'e') go(diff_scatter_staged<CT, MODE, 6, false, true, true>);
+            else if (P->stage_packed) go(diff_scatter_staged<CT, MODE, 6, false, true>);
             else if (v0 == '8') go(diff_scatter_staged<CT, MODE, 8, false, false>);
             else if (v1 == 'n') go(diff_scatter_staged<CT, MODE, 6, false, false>);
             else go(diff_scatter_staged<CT, MODE, 6, true, false>);

@@ -21,6 +21,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -117,7 +120,9 @@ stage_prepare(const int32_t *__restrict__ row32, int64_t ntiles, int32_t *__rest
 // index registers; with TMA doing the wide loads the kernel needs fewer resident warps than the gather form)
 // PACKED: few colours and short windows (C <= 14, W <= 4096): the entry's colour rides in the top 4 bits of its 16-bit row
 // offset — the per-entry colour stream is not read at all (2 index bytes per entry instead of 2 + |colour|)
-template <typename CT, int MODE, int MINB, bool PREFETCH, bool PACKED>
+// EMPTYBAR: a stage is handed back to the producer through a second mbarrier (one arrival per warp) instead of a block-wide
+// __syncthreads(): warps that finished a tile go straight on to the next one (A/B variant)
+template <typename CT, int MODE, int MINB, bool PREFETCH, bool PACKED, bool EMPTYBAR = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 diff_scatter_staged(const StagedArgs a) {
   static_assert(MODE == kForward || MODE == kCentral, "staged scatter: forward / central");
@@ -128,7 +133,8 @@ diff_scatter_staged(const StagedArgs a) {
   const int kStages = a.stages;
   double *buf = reinterpret_cast<double *>(smem_raw);                       // [stages][nwin][W]
   uint64_t *full = reinterpret_cast<uint64_t *>(buf + kStages * stage_elems);
-  double *s_eps = reinterpret_cast<double *>(full + kStagesMax);            // [C]
+  uint64_t *empty = full + kStagesMax;
+  double *s_eps = reinterpret_cast<double *>(full + 2 * kStagesMax);        // [C]
   const CT *__restrict__ ecolor = reinterpret_cast<const CT *>(a.ecolor);
   const int64_t nfull = a.E / kTile;
   constexpr int kHalf = kTile / 2;
@@ -151,7 +157,7 @@ diff_scatter_staged(const StagedArgs a) {
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kThreads / 32); }
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < C; i += kThreads) s_eps[i] = a.eps[i];
@@ -211,10 +217,22 @@ diff_scatter_staged(const StagedArgs a) {
     } else {
       Jt[tid2] = va0; Jt[tid2 + 1] = va1; Jt[kHalf + tid2] = vb0; Jt[kHalf + tid2 + 1] = vb1;
     }
-    __syncthreads();                                      // every lane is done with stage s: refill it
-    if (threadIdx.x == 0) {
-      const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
-      if (nxt < nfull) issue(nxt, s);
+    if (EMPTYBAR) {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(empty + s);              // this warp is done with stage s
+      if (threadIdx.x == 0) {
+        const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
+        if (nxt < nfull) {
+          while (!mbar_try_wait(empty + s, parity)) {}                   // ... and so are the other seven: refill it
+          issue(nxt, s);
+        }
+      }
+    } else {
+      __syncthreads();                                    // every lane is done with stage s: refill it
+      if (threadIdx.x == 0) {
+        const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
+        if (nxt < nfull) issue(nxt, s);
+      }
     }
     if (++s == kStages) { s = 0; parity ^= 1u; }
   }
