@@ -1,7 +1,8 @@
 """Randomised GPU-vs-oracle parity (bit-exact): random CSC patterns (ragged columns, empty columns, supersets of the
 function's true dependence), random — not necessarily valid — colourings (shared rows inside a colour must reproduce the
 reference's "spurious" values, invalid colours must stay zero), m != n, forward / central / complex-free, f_in, dir,
-drift on/off, both scatter strategies, batched callbacks, dense-J destinations."""
+drift on/off, every scatter strategy (storage-order pass, colour-major lists per group / in one launch), small scratch
+budgets (several groups per Jacobian), batched callbacks, dense-J destinations."""
 import ctypes as C
 
 import numpy as np
@@ -40,7 +41,11 @@ def _case(rng, pkg, oracle, dev):
     if cv.max() < 1:
         cv[0] = 1
     fdtype = "forward" if rng.random() < 0.5 else "central"
-    opts = dict(no_drift=bool(rng.random() < 0.3), strategy=int(rng.integers(0, 3)), max_batch=int(rng.integers(1, 4)))
+    opts = dict(no_drift=bool(rng.random() < 0.3), strategy=int(rng.integers(0, 4)), max_batch=int(rng.integers(1, 4)))
+    if rng.random() < 0.35:
+        # a scratch budget of a few slabs: several scatter groups per Jacobian (colour-major lists: one launch per group,
+        # f(x) pre-gathered into list order; storage-order pass: ownership tests per group)
+        opts["scratch_bytes"] = int(8 * (m + 2) * (2 if fdtype == "central" else 1) * int(rng.integers(1, 4)) + 64)
     dense_J = rng.random() < 0.3
     x = torch.from_numpy(rng.uniform(-2, 2, n)).to(dev)
     colsT, coefT = np.ascontiguousarray(cols.T), np.ascontiguousarray(coef.T)
@@ -88,5 +93,5 @@ def _case(rng, pkg, oracle, dev):
 def test_random_patterns_bitexact(pkg, oracle):
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(20260924)
-    for _ in range(60):
+    for _ in range(120):
         _case(rng, pkg, oracle, dev)
