@@ -125,11 +125,11 @@ struct fdb_plan {
   double *fx_own = nullptr, *Fp = nullptr, *Fm = nullptr, *xp = nullptr, *xm = nullptr;
   int64_t slabs = 0, ldF = 0, ldx = 0, batch = 1, n_groups = 0;
   int64_t pbatch = 1;   // perturbed points built per perturb pass (>= batch): x is read once for all of them
-  // scatter strategy (CSC plans): 0 = one fused pass over J's storage order (row-local patterns), 1 = per-colour
-  // column lists launched right after the colour's f! (random patterns: the slab is gathered from L2; multi-GPU)
+  // scatter form of a CSC plan (internal; opts->strategy 0..3 is mapped onto it in fdb_plan_create_csc):
+  // 0 = one fused pass over J's storage order, 1 = colour-major entry lists (per group of resident colours)
   int strategy = 0;
   bool strategy_auto = true;
-  bool lists_resident = false;         // strategy 1 with every local colour's f! output resident: ONE launch over the lists
+  bool lists_resident = false;         // lists with every local colour's f! output resident: ONE launch over them
   // A/B switches (environment, read ONCE when the plan is created — never on the hot path)
   struct Tunables {
     bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
@@ -776,7 +776,11 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     // ext/FiniteDiffSparseArraysExt.jl:51-52
     PLAN_TRY(view_i64(j_colptr, n + 1, jcp));
     int64_t jlast = 1;
-    cudaMemcpy(&jlast, jcp.d + n, 8, cudaMemcpyDeviceToHost);
+    {
+      cudaError_t e = cudaMemcpy(&jlast, jcp.d + n, 8, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_CUDA, "reading J.colptr[n]: %s", cudaGetErrorString(e)); }
+    }
+    if (jlast < 1 || jlast - 1 > 0x7FFFFFF0LL) { free_plan(P); *plan = nullptr; return fail(FDB_ERR_INVALID, "J.colptr[n+1]=%lld is not a valid CSC end pointer", (long long)jlast); }
     const int64_t jnnz = jlast - 1;
     PLAN_TRY(view_i64(j_rowval, jnnz, jrv));
     if (jnnz != nnz) same_pattern = false;
@@ -805,6 +809,10 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
   }
   validate_colptr<<<P->grid(n + 1), kThreads>>>(cp.d, n, nnz, d_err);
   PLAN_TRY(read_plan_err(d_err, "CSC sparsity"));
+  if (other_csc) {   // J's own column pointer is searched by dest_other_csc: it must be a valid one too
+    validate_colptr<<<P->grid(n + 1), kThreads>>>(jcp.d, n, P->j_len, d_err);
+    PLAN_TRY(read_plan_err(d_err, "J's CSC pattern"));
+  }
   if (nnz > 0) {
     PLAN_TRY(dispatch_ct(P->color_bits, [&](auto tag) -> fdb_status {
       using CT = decltype(tag);
@@ -857,11 +865,10 @@ fdb_status fdb_plan_create_csc(fdb_plan **plan, int64_t m, int64_t n, const int6
     const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
     while (lanes < 32 && lanes < avg) lanes *= 2;
     P->lanes = lanes;
-    // strategy: opts->strategy 1 = fused, 2 = per-colour lists, 0 = auto.  Measured on B200 (profiles/r1): on ONE GPU
-    // the fused pass wins even for random patterns (C4: 1.39 ms vs 64 x 29 us) — every 64-byte line of a slab is
-    // fetched once either way and the fused launch keeps f(x) L2-resident; the lists win whenever a launch would
-    // otherwise stream entries it does not own: several ranks sharing the colours, or more colours than resident
-    // slabs (decided in finish_colored_plan).
+    // opts->strategy: 0 auto, 1 fused storage-order pass, 2 colour-major lists launched per group of resident colours,
+    // 3 colour-major lists with every slab resident (one launch).  The lists are what a launch needs whenever it would
+    // otherwise stream entries it does not own: several ranks sharing the colours, or more colours than resident slabs
+    // (the latter is decided in finish_colored_plan).
     const int want = opts ? opts->strategy : 0;
     bool per_color = P->world > 1;
     if (want == 1) per_color = false;

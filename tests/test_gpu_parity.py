@@ -661,6 +661,13 @@ def test_different_pattern_csc_J(pkg, oracle, dev):
         pkg.finite_difference_jacobian_(Jsub, native(pkg, "fdbs_tridiag", pkg._lib.TridiagCtx(N, 0)), x,
                                         pkg.JacobianCache(x, "forward", colorvec=cyc_colors(N, 3), sparsity=sp))
     assert ei.value.status == pkg._lib.FDB_ERR_UNSUPPORTED
+    # J's own column pointer is searched by the plan: a decreasing one is rejected, not read out of bounds
+    bad = pkg.SparseMatrixCSC.from_scipy(Afull, dev)
+    bad.colptr[N // 2] = bad.colptr[N // 2 + 1] + 3
+    with pytest.raises(pkg._lib.FdbError) as ei:
+        pkg.finite_difference_jacobian_(bad, native(pkg, "fdbs_tridiag", pkg._lib.TridiagCtx(N, 0)), x,
+                                        pkg.JacobianCache(x, "forward", colorvec=cyc_colors(N, 3), sparsity=sp))
+    assert ei.value.status == pkg._lib.FDB_ERR_INVALID
 
 
 @pytest.mark.parametrize("fdtype", ["forward", "central"])
