@@ -592,7 +592,7 @@ def run_single(pkg, workload, fdtype, dev, args, steps, spin_s=0.0, strategy=0, 
     f_points = m["c1"]["f_points"] - m["c0"]["f_points"]
     lib_launches = m["c1"]["kernel_launches"] - m["c0"]["kernel_launches"]
     f_inv = m["c1"]["f_invocations"] - m["c0"]["f_invocations"]
-    f_launch_per_point = {"c5": 2}.get(workload, 1)
+    f_launch_per_point = {"c5": 3}.get(workload, 1)
     key = traffic_key(workload, fdtype, info)
     roof_kernel = scatter_kernel_name(info, fdtype)
     rec = {
@@ -846,7 +846,7 @@ def gpu_arm_multi(args, pkg, dev, rank, world):
     f_points_all = dist_sum(m["c1"]["f_points"] - m["c0"]["f_points"])
     lib_launches = m["c1"]["kernel_launches"] - m["c0"]["kernel_launches"]
     f_inv = m["c1"]["f_invocations"] - m["c0"]["f_invocations"]
-    gpu_launches = lib_launches + f_inv * {"c5": 2}.get(workload, 1)
+    gpu_launches = lib_launches + f_inv * {"c5": 3}.get(workload, 1)
     key = traffic_key(workload, fdtype, info)
     roofline = roofline_record(info, fdtype, m["scat_ms"], m["scat_n"], m["tsteps"], key)
 

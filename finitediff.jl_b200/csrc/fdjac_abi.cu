@@ -135,6 +135,7 @@ struct fdb_plan {
     bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
     bool no_fx_cm = false, force_fx_cm = false, no_pack = false;
     int hi_stream = -1;                // -1: by pattern (random => evict-first slab gathers), 0 / 1: forced
+    int cols_depth = 0, cols_gx = 64;  // diff_columns: loads in flight per thread (0 = by mode) / cap on the row blocks per column
     int stages = 2;
     char staged_variant[3] = {'6', 'n', 0};
   } tune;
@@ -638,6 +639,10 @@ static void read_tunables(fdb_plan *P) {
   t.no_pack = env_is("FDB_NO_PACK", '1');
   if (const char *hs = getenv("FDB_HI_STREAM")) t.hi_stream = hs[0] == '1' ? 1 : 0;
   if (env_is("FDB_STAGES", '3')) t.stages = 3;
+  if (env_is("FDB_COLS_DEPTH", '4')) t.cols_depth = 4;
+  if (env_is("FDB_COLS_DEPTH", '2')) t.cols_depth = 2;
+  if (env_is("FDB_COLS_DEPTH", '1')) t.cols_depth = 1;
+  if (const char *v = getenv("FDB_COLS_GX")) { const int g = atoi(v); if (g >= 1 && g <= 4096) t.cols_gx = g; }
   if (const char *v = getenv("FDB_STAGED_VARIANT")) {
     if (v[0]) { t.staged_variant[0] = v[0]; t.staged_variant[1] = v[1] ? v[1] : 'n'; }
   }
@@ -1621,15 +1626,20 @@ static fdb_status run_dense(fdb_plan *P, fdb_fn f, void *ctx, const double *x, d
     }
     // a store-heavy stream (24 bytes moved per 8 written): many small blocks rather than one resident wave — each thread
     // handles about four row pairs (see the band kernel's grid note)
-    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((P->m / 2 + kThreads * 4 - 1) / (kThreads * 4), 64));
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((P->m / 2 + kThreads * 4 - 1) / (kThreads * 4), P->tune.cols_gx));
     dim3 grid((unsigned)gx, (unsigned)kc);
     {
       const double *lo_ptr = CENTRAL ? P->Fm : vfx;
       const int pairs_ok = ((reinterpret_cast<uintptr_t>(J + c0l * P->ldJ) | reinterpret_cast<uintptr_t>(lo_ptr) |
                              reinterpret_cast<uintptr_t>(P->Fp)) & 15) == 0 && (P->ldJ & 1) == 0 && (sF & 1) == 0;
       ScatterTimer tm(P, s);
-      diff_columns<MODE><<<grid, kThreads, 0, s>>>(P->Fp, lo_ptr, P->eps_cols, c0l, kc, P->m, sF, P->ldJ,
-                                                   J + c0l * P->ldJ, pairs_ok);
+      auto go = [&](auto kern) { kern<<<grid, kThreads, 0, s>>>(P->Fp, lo_ptr, P->eps_cols, c0l, kc, P->m, sF, P->ldJ, J + c0l * P->ldJ, pairs_ok); };
+      // independent 16-byte loads in flight per thread before the first quotient (same box, C5 shape, us per 256-column
+      // launch, depth 1 / 2 / 4: central 112.1 / 95.6 / 94.8, forward 88.1 / 74.3 / 76.2; profiles/r2_ab7.txt)
+      const int depth = P->tune.cols_depth ? P->tune.cols_depth : (CENTRAL ? 4 : 2);
+      if (depth == 4) go(diff_columns<MODE, 4>);
+      else if (depth == 2) go(diff_columns<MODE, 2>);
+      else go(diff_columns<MODE, 1>);
     }
     P->cnt.kernel_launches += 2;
     P->cnt.scatter_launches += 1;

@@ -635,7 +635,7 @@ diff_scatter_band(const BandArgs a) {
 
 // ---- dense column branch: J[:, c] = (fx1 - fx)/eps_c (jacobians.jl:555), (fx1 - fx_minus)/(2 eps_c) (:597),
 //      imag(fx)/eps (:630) ----
-template <int MODE>
+template <int MODE, int DEPTH = 1>
 __global__ void __launch_bounds__(kThreads)
 diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx, const double *__restrict__ eps_local,
              int64_t col0_local, int32_t B, int64_t m, int64_t ldF, int64_t ldJ, double *__restrict__ Jcols,
@@ -653,7 +653,23 @@ diff_columns(const double *__restrict__ Fp, const double *__restrict__ Fm_or_fx,
     // f(x) (forward) is re-read by every column and stays cacheable
     const double denom = MODE == kCentral ? 2 * e : e;
     const int64_t m2 = m >> 1;
-    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < m2; i += stride) {
+    int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    if (DEPTH > 1) {
+      // DEPTH independent 16-byte loads of each slab in flight before the first quotient is formed
+      for (; i + (DEPTH - 1) * stride < m2; i += DEPTH * stride) {
+        double2 h[DEPTH], l[DEPTH];
+#pragma unroll
+        for (int q = 0; q < DEPTH; ++q) {
+          h[q] = ld_stream2(hi + 2 * (i + q * stride));
+          l[q] = MODE == kCentral ? ld_stream2(lo + 2 * (i + q * stride))
+                                  : __ldg(reinterpret_cast<const double2 *>(lo + 2 * (i + q * stride)));
+        }
+#pragma unroll
+        for (int q = 0; q < DEPTH; ++q)
+          st_stream2(out + 2 * (i + q * stride), (h[q].x - l[q].x) / denom, (h[q].y - l[q].y) / denom);
+      }
+    }
+    for (; i < m2; i += stride) {
       const double2 h = ld_stream2(hi + 2 * i);
       const double2 l = MODE == kCentral ? ld_stream2(lo + 2 * i) : __ldg(reinterpret_cast<const double2 *>(lo + 2 * i));
       st_stream2(out + 2 * i, (h.x - l.x) / denom, (h.y - l.y) / denom);

@@ -3,6 +3,7 @@
 #include "../../include/fdjac_synth.h"
 
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace {
 constexpr int kT = 256;
@@ -90,20 +91,43 @@ __global__ void __launch_bounds__(kT) k_block_sums(const double *__restrict__ x,
   }
 }
 
+// S[p] = (block sums of point p added in block order) / n, left in bs[p*nblk] (only thread p touches row p)
+__global__ void __launch_bounds__(kT) k_point_sums(double *__restrict__ bs, int64_t nblk, int64_t n, int64_t batch) {
+  const int64_t p = blockIdx.x * (int64_t)kT + threadIdx.x;
+  if (p >= batch) return;
+  double t = 0.0;
+  for (int64_t b = 0; b < nblk; ++b) t = add(t, bs[p * nblk + b]);
+  bs[p * nblk] = __ddiv_rn(t, (double)n);
+}
+
 __global__ void __launch_bounds__(kT) k_rank1(double *__restrict__ fx, const double *__restrict__ x, int64_t n,
                                               const double *__restrict__ w, const double *__restrict__ bs, int64_t nblk,
-                                              int64_t ldfx, int64_t ldx) {
+                                              int64_t ldfx, int64_t ldx, int vec_ok) {
   const double *xb = x + (int64_t)blockIdx.y * ldx;
   double *fb = fx + (int64_t)blockIdx.y * ldfx;
-  __shared__ double S;
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int64_t b = 0; b < nblk; ++b) t = add(t, bs[(int64_t)blockIdx.y * nblk + b]);
-    S = __ddiv_rn(t, (double)n);
+  const double s = __ldg(bs + (int64_t)blockIdx.y * nblk);
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  if (vec_ok) {
+    // two rows per lane, two independent 16-byte loads of x in flight; x and f are read / written once (streaming), w is
+    // shared by every point of the batch (cacheable)
+    const int64_t n2 = n >> 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(xb), *w2 = reinterpret_cast<const double2 *>(w);
+    double2 *f2 = reinterpret_cast<double2 *>(fb);
+    int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+    for (; i + stride < n2; i += 2 * stride) {
+      const double2 a = __ldcs(x2 + i), b = __ldcs(x2 + i + stride);
+      const double2 wa = __ldg(w2 + i), wb = __ldg(w2 + i + stride);
+      __stcs(f2 + i, make_double2(add(mul(a.x, a.x), mul(wa.x, s)), add(mul(a.y, a.y), mul(wa.y, s))));
+      __stcs(f2 + i + stride, make_double2(add(mul(b.x, b.x), mul(wb.x, s)), add(mul(b.y, b.y), mul(wb.y, s))));
+    }
+    for (; i < n2; i += stride) {
+      const double2 a = __ldcs(x2 + i), wa = __ldg(w2 + i);
+      __stcs(f2 + i, make_double2(add(mul(a.x, a.x), mul(wa.x, s)), add(mul(a.y, a.y), mul(wa.y, s))));
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const double v = xb[n - 1]; fb[n - 1] = add(mul(v, v), mul(w[n - 1], s)); }
+    return;
   }
-  __syncthreads();
-  const double s = S;
-  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < n; i += stride) {
     const double v = xb[i];
     fb[i] = add(mul(v, v), mul(w[i], s));
   }
@@ -244,8 +268,11 @@ int fdbs_rank1(void *vctx, double *d_fx, const double *d_x, int64_t batch, int64
   const int64_t nblk = (c->n + 1023) / 1024;
   dim3 g1((unsigned)blocks_for(nblk * 32, 64), (unsigned)batch);   // one warp per 1024-block
   k_block_sums<<<g1, kT, 0, (cudaStream_t)stream>>>(d_x, c->n, ldx, c->d_block_sums, nblk);
-  dim3 g2((unsigned)blocks_for(c->n, 64), (unsigned)batch);
-  k_rank1<<<g2, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, c->d_w, c->d_block_sums, nblk, ldfx, ldx);
+  k_point_sums<<<(unsigned)((batch + kT - 1) / kT), kT, 0, (cudaStream_t)stream>>>(c->d_block_sums, nblk, c->n, batch);
+  // 16-byte path: every point / output / w base 16-byte aligned (even leading dimensions)
+  const int vec_ok = (((uintptr_t)d_x | (uintptr_t)d_fx | (uintptr_t)c->d_w) & 15) == 0 && (ldx & 1) == 0 && (ldfx & 1) == 0;
+  dim3 g2((unsigned)blocks_for((c->n + 3) / 4, 128), (unsigned)batch);
+  k_rank1<<<g2, kT, 0, (cudaStream_t)stream>>>(d_fx, d_x, c->n, c->d_w, c->d_block_sums, nblk, ldfx, ldx, vec_ok);
   return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
 

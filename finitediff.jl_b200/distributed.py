@@ -122,6 +122,7 @@ class DeviceBarrier:
 
     def __init__(self, device, group=None):
         self.device = torch.device(device)
+        self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -162,7 +163,7 @@ class DeviceBarrier:
                 L.lib().fdb_ipc_close(C.c_void_p(p))
             self._mapped = []
         try:
-            dist.barrier()
+            dist.barrier(group=self.group)       # nobody frees a flag block a peer may still signal
         except Exception:
             pass
         L.lib().fdb_sync_destroy(self._h)
