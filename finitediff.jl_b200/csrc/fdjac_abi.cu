@@ -135,6 +135,7 @@ struct fdb_plan {
     bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
     bool no_fx_cm = false, force_fx_cm = false, no_pack = false;
     int hi_stream = -1;                // -1: by pattern (random => evict-first slab gathers), 0 / 1: forced
+    int eps_depth = 2;                 // color_sumsq_reg: tiles of loads in flight per thread (same summation order, same bits)
     int cols_depth = 0, cols_gx = 64;  // diff_columns: loads in flight per thread (0 = by mode) / cap on the row blocks per column
     int stages = 2;
     char staged_variant[3] = {'6', 'n', 0};
@@ -639,6 +640,7 @@ static void read_tunables(fdb_plan *P) {
   t.no_pack = env_is("FDB_NO_PACK", '1');
   if (const char *hs = getenv("FDB_HI_STREAM")) t.hi_stream = hs[0] == '1' ? 1 : 0;
   if (env_is("FDB_STAGES", '3')) t.stages = 3;
+  if (env_is("FDB_EPS_DEPTH", '1')) t.eps_depth = 1;   // C2 central step 396.4 -> 395.2 us with 2 (profiles/r2_ab8.txt); forward: noise
   if (env_is("FDB_COLS_DEPTH", '4')) t.cols_depth = 4;
   if (env_is("FDB_COLS_DEPTH", '2')) t.cols_depth = 2;
   if (env_is("FDB_COLS_DEPTH", '1')) t.cols_depth = 1;
@@ -1279,15 +1281,12 @@ static fdb_status run_eps(fdb_plan *P, const double *x, double relstep, double a
   if (C <= kEpsRegColors) {
     const int64_t ntiles = (P->n + kTile - 1) / kTile;
     const int aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    if (C <= 4) {
-      int grid = std::min(resident_grid(P, color_sumsq_reg<CT, 4>, 0, ntiles), P->eps_blocks);  // partial capacity
-      color_sumsq_reg<CT, 4><<<grid, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, aligned, C, prm, P->partial,
-                                                        P->ticket, P->eps, P->sumsq);
-    } else {
-      int grid = std::min(resident_grid(P, color_sumsq_reg<CT, 8>, 0, ntiles), P->eps_blocks);
-      color_sumsq_reg<CT, 8><<<grid, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, aligned, C, prm, P->partial,
-                                                        P->ticket, P->eps, P->sumsq);
-    }
+    auto go = [&](auto kern) {
+      const int grid = std::min(resident_grid(P, kern, 0, ntiles), P->eps_blocks);  // partial capacity
+      kern<<<grid, kThreads, 0, s>>>(x, (const CT *)P->jcolor, P->n, aligned, C, prm, P->partial, P->ticket, P->eps, P->sumsq);
+    };
+    if (C <= 4) { if (P->tune.eps_depth == 2) go(color_sumsq_reg<CT, 4, 2>); else go(color_sumsq_reg<CT, 4, 1>); }
+    else { if (P->tune.eps_depth == 2) go(color_sumsq_reg<CT, 8, 2>); else go(color_sumsq_reg<CT, 8, 1>); }
     P->cnt.kernel_launches += 1;
   } else {
     for (int32_t k0 = 0; k0 < C; k0 += kEpsWindow) {

@@ -44,7 +44,7 @@ __device__ __forceinline__ void sumsq_accumulate(double (&acc)[NC], double v, ui
     if (c == (uint32_t)k) acc[k] += sq;
 }
 
-template <typename CT, int NC>
+template <typename CT, int NC, int DEPTH = 1>
 __global__ void __launch_bounds__(kThreads)
 color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int64_t n, int x_aligned, int32_t C,
                 EpsParams prm, double *__restrict__ partial /* [gridDim.x][kEpsRegColors] */,
@@ -55,7 +55,30 @@ color_sumsq_reg(const double *__restrict__ x, const CT *__restrict__ jcolor, int
   constexpr int kHalf = kTile / 2;
   const int64_t nfull = x_aligned ? n / kTile : 0;
   const int tid2 = 2 * threadIdx.x;
-  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
+  int64_t tile = blockIdx.x;
+  if (DEPTH == 2) {
+    // two tiles' loads in flight; accumulated in the same order as the one-tile loop (tile, then tile + gridDim.x)
+    for (; tile + gridDim.x < nfull; tile += 2 * (int64_t)gridDim.x) {
+      const double *__restrict__ xa = x + tile * kTile, *__restrict__ xb = xa + (int64_t)gridDim.x * kTile;
+      const CT *__restrict__ ca = jcolor + tile * kTile, *__restrict__ cb = ca + (int64_t)gridDim.x * kTile;
+      const double2 a0 = ld_stream2(xa + tid2), a1 = ld_stream2(xa + kHalf + tid2);
+      const double2 b0 = ld_stream2(xb + tid2), b1 = ld_stream2(xb + kHalf + tid2);
+      uint32_t p0, p1, p2, p3, q0, q1, q2, q3;
+      ld_color_pair<CT>(ca + tid2, p0, p1);
+      ld_color_pair<CT>(ca + kHalf + tid2, p2, p3);
+      ld_color_pair<CT>(cb + tid2, q0, q1);
+      ld_color_pair<CT>(cb + kHalf + tid2, q2, q3);
+      sumsq_accumulate<NC>(acc, a0.x, p0);
+      sumsq_accumulate<NC>(acc, a0.y, p1);
+      sumsq_accumulate<NC>(acc, a1.x, p2);
+      sumsq_accumulate<NC>(acc, a1.y, p3);
+      sumsq_accumulate<NC>(acc, b0.x, q0);
+      sumsq_accumulate<NC>(acc, b0.y, q1);
+      sumsq_accumulate<NC>(acc, b1.x, q2);
+      sumsq_accumulate<NC>(acc, b1.y, q3);
+    }
+  }
+  for (; tile < nfull; tile += gridDim.x) {
     const double *__restrict__ xt = x + tile * kTile;
     const CT *__restrict__ ct = jcolor + tile * kTile;
     const double2 va = ld_stream2(xt + tid2);
