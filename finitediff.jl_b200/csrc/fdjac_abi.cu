@@ -135,6 +135,11 @@ struct fdb_plan {
     bool no_staged = false, no_eps_lists = false, no_eps_overlap = false, cm_prefetch = false, force_overlap = false;
     bool no_fx_cm = false, force_fx_cm = false, no_pack = false;
     int hi_stream = -1;                // -1: by pattern (random => evict-first slab gathers), 0 / 1: forced
+    // walk direction (r2 A/B 9, C2 step forward / central: 0.2790 / 0.3961 -> 0.2757 / 0.3916 ms): bit 0 the staged scatter
+    // starts at the END of J's storage, bit 1 the perturbation pass at the end of x — each reads first what the kernel
+    // before it streamed last (still in L2), and the first f! finds the heads of the points the perturbation wrote last
+    int reverse = 3;
+    int cm_slab_stream = 1;            // colour-major scatter, forward: slab gathers evict-first (CmArgs::slab_stream)
     int eps_depth = 2;                 // color_sumsq_reg: tiles of loads in flight per thread (same summation order, same bits)
     int cols_depth = 0, cols_gx = 64;  // diff_columns: loads in flight per thread (0 = by mode) / cap on the row blocks per column
     int stages = 2;
@@ -639,6 +644,8 @@ static void read_tunables(fdb_plan *P) {
   t.force_fx_cm = env_is("FDB_FORCE_FX_CM", '1');
   t.no_pack = env_is("FDB_NO_PACK", '1');
   if (const char *hs = getenv("FDB_HI_STREAM")) t.hi_stream = hs[0] == '1' ? 1 : 0;
+  if (const char *v = getenv("FDB_REVERSE")) { if (v[0] >= '0' && v[0] <= '3') t.reverse = v[0] - '0'; }
+  if (env_is("FDB_CM_HINT", '0')) t.cm_slab_stream = 0;
   if (env_is("FDB_STAGES", '3')) t.stages = 3;
   if (env_is("FDB_EPS_DEPTH", '1')) t.eps_depth = 1;   // C2 central step 396.4 -> 395.2 us with 2 (profiles/r2_ab8.txt); forward: noise
   if (env_is("FDB_COLS_DEPTH", '4')) t.cols_depth = 4;
@@ -1357,6 +1364,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
         pa.x = x; pa.jcolor = P->jcolor; pa.eps = P->eps;
         pa.xp = P->xp + q0 * sX; pa.xm = CENTRAL ? P->xm + q0 * sX : nullptr;
         pa.n = P->n; pa.ldx = sX; pa.C = P->C; pa.drift = P->no_drift ? 0 : 1;
+        pa.reverse = (P->tune.reverse >> 1) & 1;
         pa.kcount = (int32_t)std::min<int64_t>(kPerturbMaxPoints, kc - q0);
         for (int32_t q = 0; q < pa.kcount; ++q) pa.k[q] = P->local_colors[(size_t)(li0 + q0 + q)];
         pa.aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(P->xp) |
@@ -1410,6 +1418,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
     // (software L2 prefetch of the next colour's slab: measured SLOWER on C4 — 1.255 vs 0.962 ms — the 40 MB slab, the next
     //  one and f(x) do not fit the L2 together; off unless FDB_CM_PREFETCH=1)
     a.prefetch_next = (G > 1 && P->tune.cm_prefetch) ? 1 : 0;
+    a.slab_stream = P->tune.cm_slab_stream;
     const int64_t tiles = (total + kCmTile - 1) / kCmTile;
     ScatterTimer tm(P, ss);
     if (wide) {
@@ -1512,6 +1521,7 @@ static fdb_status run_colored(fdb_plan *P, fdb_fn f, void *ctx, const double *x,
             sa.row16 = P->row16; sa.ecolor = P->ecolor; sa.tile_w0 = P->tile_w0; sa.row32 = P->row32;
             sa.fx = vfx; sa.Fp = P->Fp; sa.Fm = P->Fm; sa.eps = P->eps; sa.J = J; sa.C = P->C; sa.W = P->stage_W;
             sa.ldF = sF; sa.src_len = P->ldF; sa.E = P->E; sa.j_aligned = a.j_aligned;
+            sa.reverse = P->tune.reverse & 1;
             const int nwin = CENTRAL ? 2 * P->C : P->C + 1;
             int stages = P->tune.stages;
             if ((size_t)stages * nwin * P->stage_W * 8 + 2 * kStagesMax * 8 + (size_t)P->C * 8 > (size_t)kStageMaxSmem) stages = 2;

@@ -30,6 +30,8 @@ struct PerturbArgs {
   int32_t C, drift, kcount;
   int32_t k[kPerturbMaxPoints];   // global colour id of each point
   int32_t aligned;                // x, xp, xm 16-byte aligned and ldx even
+  int32_t reverse;                // walk the full tiles from the end of x to its start (the tail of x is what the pass
+                                  // before left in L2; the heads of the points are what the first f! reads first)
 };
 
 template <bool CENTRAL>
@@ -62,8 +64,8 @@ perturb_colors(const PerturbArgs a) {
   auto eps_of = [&](uint32_t c) -> double {
     return c < (uint32_t)a.C ? (use_smem ? s_eps[c] : __ldg(a.eps + c)) : 0.0;
   };
-  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x) {
-    const int64_t base = tile * kTile;
+  for (int64_t pos = blockIdx.x; pos < nfull; pos += gridDim.x) {
+    const int64_t base = (a.reverse ? nfull - 1 - pos : pos) * kTile;
     const double2 va = ld_stream2(a.x + base + tid2);
     const double2 vb = ld_stream2(a.x + base + kHalf + tid2);
     uint32_t ca0, ca1, cb0, cb1;

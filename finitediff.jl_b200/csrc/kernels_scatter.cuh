@@ -234,6 +234,9 @@ struct CmArgs {
   int32_t prefetch_next;       // several resident colours in one launch: while the tiles of colour s are processed, the
                                // grid streams slab s+1 into L2 (prefetch.global.L2, one pass, sequential) — the random
                                // 8-byte gathers of the next colour then hit L2 instead of fetching a DRAM granule each
+  int32_t slab_stream;         // forward, f(x) gathered by row: the slab values are read once -> evict-first loads (ld.cs), so
+                               // that they do not push f(x) — re-read by every colour — out of L2 (r2 A/B 9, C4 one launch:
+                               // 1.176 -> 1.020 ms; createpolicy evict-last on f(x) + no-L1 evict-first on the slab: 1.075)
   int64_t m;                   // rows of a slab (prefetch extent)
   int64_t ldF;
 };
@@ -298,7 +301,7 @@ diff_scatter_cm(const CmArgs a) {
         const double *lo_p = MODE == kCentral ? a.Fm + (int64_t)seg * a.ldF : a.fx;
         if (lo_stream)
           v[u] = (__ldcs(hi_p + r[u]) - lo_v[u]) / s_eps[seg];              // same IEEE subtraction and division
-        else if (MODE == kForward && a.prefetch_next)                        // read-once slab values: evict-first, f(x) stays
+        else if (MODE == kForward && (a.slab_stream || a.prefetch_next))     // read-once slab values: evict-first, f(x) stays
           v[u] = (__ldcs(hi_p + r[u]) - __ldg(lo_p + r[u])) / s_eps[seg];
         else
           v[u] = fd_quotient<MODE>(hi_p, lo_p, r[u], s_eps[seg]);          // fused with ext/..SparseArraysExt.jl:44

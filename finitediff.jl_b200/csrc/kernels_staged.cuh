@@ -64,6 +64,8 @@ struct StagedArgs {
   int64_t ldF, src_len;      // slab stride; readable doubles behind fx / every slab (even)
   int64_t E;
   int32_t j_aligned;
+  int32_t reverse;           // walk the full tiles from the end of J's storage towards its start: the rows the last f! wrote
+                             // most recently (the tail of the last slab) are read while they are still in L2
 };
 
 // plan time: window start (even) of every full tile, 16-bit offsets, largest span
@@ -139,6 +141,8 @@ diff_scatter_staged(const StagedArgs a) {
   const int64_t nfull = a.E / kTile;
   constexpr int kHalf = kTile / 2;
   const int tid2 = 2 * threadIdx.x;
+  // position in the walk -> tile of J's storage (the walk order is free: every tile is independent)
+  auto phys = [&](int64_t t) -> int64_t { return a.reverse ? nfull - 1 - t : t; };
 
   // one thread feeds the pipeline: nwin bulk copies per tile, all completing on the stage's mbarrier
   auto issue = [&](int64_t tile, int s) {
@@ -165,7 +169,7 @@ diff_scatter_staged(const StagedArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (t < nfull) issue(t, s);
+      if (t < nfull) issue(phys(t), s);
     }
   }
 
@@ -200,11 +204,12 @@ diff_scatter_staged(const StagedArgs a) {
   int s = 0;
   uint32_t parity = 0;
   Idx nx{};
-  if (PREFETCH && (int64_t)blockIdx.x < nfull) nx = load_idx(blockIdx.x);
-  for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, ++it) {
+  if (PREFETCH && (int64_t)blockIdx.x < nfull) nx = load_idx(phys(blockIdx.x));
+  for (int64_t pos = blockIdx.x; pos < nfull; pos += gridDim.x, ++it) {
+    const int64_t tile = phys(pos);
     double *__restrict__ Jt = a.J + tile * kTile;
     const Idx cur = PREFETCH ? nx : load_idx(tile);
-    if (PREFETCH && tile + gridDim.x < nfull) nx = load_idx(tile + gridDim.x);
+    if (PREFETCH && pos + gridDim.x < nfull) nx = load_idx(phys(pos + gridDim.x));
     const ushort2 ra = cur.ra, rb = cur.rb;
     const uint32_t ka0 = cur.ka0, ka1 = cur.ka1, kb0 = cur.kb0, kb1 = cur.kb1;
     while (!mbar_try_wait(full + s, parity)) {}
@@ -221,17 +226,17 @@ diff_scatter_staged(const StagedArgs a) {
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbar_arrive(empty + s);              // this warp is done with stage s
       if (threadIdx.x == 0) {
-        const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
+        const int64_t nxt = pos + (int64_t)kStages * gridDim.x;
         if (nxt < nfull) {
           while (!mbar_try_wait(empty + s, parity)) {}                   // ... and so are the other seven: refill it
-          issue(nxt, s);
+          issue(phys(nxt), s);
         }
       }
     } else {
       __syncthreads();                                    // every lane is done with stage s: refill it
       if (threadIdx.x == 0) {
-        const int64_t nxt = tile + (int64_t)kStages * gridDim.x;
-        if (nxt < nfull) issue(nxt, s);
+        const int64_t nxt = pos + (int64_t)kStages * gridDim.x;
+        if (nxt < nfull) issue(phys(nxt), s);
       }
     }
     if (++s == kStages) { s = 0; parity ^= 1u; }
