@@ -101,3 +101,17 @@ def test_product_never_imports_oracle():
             txt = p.read_text()
             assert "fd_oracle" not in txt and "libfd_oracle" not in txt, p
             assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), p
+
+
+def test_every_environment_switch_is_documented():
+    """The A/B switches are read with getenv when a plan is created; DESIGN.md §4 is the only place a user can learn about
+    them — a switch added to the sources must appear in that table."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    names = set()
+    for src in sorted((root / "finitediff.jl_b200" / "csrc").glob("*.cu*")):
+        names |= set(re.findall(r'(?:getenv|env_is)\("(FDB[A-Z_0-9]*)"', src.read_text()))
+    assert names, "no switches found: the scan is broken"
+    design = (root / "DESIGN.md").read_text()
+    missing = sorted(n for n in names if n not in design)
+    assert not missing, f"undocumented environment switches: {missing}"
