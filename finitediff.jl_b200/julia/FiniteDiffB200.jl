@@ -200,10 +200,12 @@ function plan_csc(sp::SparseMatrixCSC{Float64, Int64}, Jhost, ldJ::Integer, colo
 end
 
 # structural-nonzero lists (Tridiagonal / dense prototype): generic hook src/iteration_utils.jl:25-32
-function plan_coo(anchor, m::Integer, n::Integer, rows::Vector{Int64}, cols::Vector{Int64}, jk::Cint,
-        slots::Union{Nothing, Vector{Int64}}, ld_or_len::Integer, colorvec, fd::Cint; kw...)
-    key = (:coo, m, n, length(rows), jk, ld_or_len, color_key(colorvec), fd, values(kw))
+# `structure()` returns (rows, cols, slots-or-nothing); it runs only when the plan is not cached yet, so a cached call does
+# no O(nnz) host work (the reference rebuilds these lists on every call, jacobians.jl:522-528)
+function plan_coo(structure::Function, anchor, m::Integer, n::Integer, tag, jk::Cint, ld_or_len::Integer, colorvec, fd::Cint; kw...)
+    key = (:coo, m, n, tag, jk, ld_or_len, color_key(colorvec), fd, values(kw))
     cached_plan(anchor, key) do
+        rows, cols, slots = structure()
         h = Ref{Ptr{Cvoid}}(C_NULL)
         opts = Ref(PlanOpts(fd; kw...))
         cptr, croot = color_arg(colorvec, n)
@@ -337,8 +339,7 @@ function plan_for(J::DeviceBanded, sp, colorvec, fd)
     (plan_banded(J.data, J.m, J.n, J.l, J.u, FDB_J_BAND, 0, colorvec, fd), J.data)
 end
 function plan_for(J::DeviceTridiagonal, sp, colorvec, fd)
-    rows, cols, slots = tridiagonal_structure(J.n)
-    (plan_coo(J.buf, J.n, J.n, rows, cols, FDB_J_SLOTS, slots, 3 * J.n - 2, colorvec, fd), J.buf)
+    (plan_coo(() -> tridiagonal_structure(J.n), J.buf, J.n, J.n, :tridiagonal, FDB_J_SLOTS, 3 * J.n - 2, colorvec, fd), J.buf)
 end
 function plan_for(J::CuMatrix{Float64}, sp, colorvec, fd)
     m, n = size(J)
@@ -350,11 +351,16 @@ function plan_for(J::CuMatrix{Float64}, sp, colorvec, fd)
     elseif sp isa DeviceBanded                                          # ext/..BandedMatricesExt.jl:13-27, dense target
         return (plan_banded(J, m, n, sp.l, sp.u, FDB_J_DENSE, ld(J), colorvec, fd), J)
     elseif sp isa DeviceTridiagonal
-        rows, cols, _ = tridiagonal_structure(sp.n)
-        return (plan_coo(J, m, n, rows, cols, FDB_J_DENSE, nothing, ld(J), colorvec, fd), J)
+        return (plan_coo(J, m, n, :tridiagonal, FDB_J_DENSE, ld(J), colorvec, fd) do
+                rows, cols, _ = tridiagonal_structure(sp.n)
+                (rows, cols, nothing)
+            end, J)
     elseif sp isa AbstractMatrix                                        # dense 0/1 prototype, jacobians.jl:526-527
-        rows, cols = dense_prototype_structure(sp)
-        return (plan_coo(J, m, n, rows, cols, FDB_J_DENSE, nothing, ld(J), colorvec, fd), J)
+        # keyed on the prototype's identity: editing it in place needs a new array (as for every cached pattern)
+        return (plan_coo(J, m, n, (:prototype, objectid(sp)), FDB_J_DENSE, ld(J), colorvec, fd) do
+                rows, cols = dense_prototype_structure(sp)
+                (rows, cols, nothing)
+            end, J)
     end
     throw(ArgumentError("unsupported sparsity type $(typeof(sp))"))
 end
