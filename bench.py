@@ -237,6 +237,7 @@ def cpu_jacobian_runner(workload, fdtype, nthreads, scale=1.0):
         def run(eps_override=None):
             return orc.jacobian(P, nz, fn, x, fdtype=fd, colorvec=cv, nthreads=nthreads, ctx=ctx, cache=cache,
                                 eps_override=eps_override)["fcalls"], nz
+        run.x, run.cv, run.fd = x, cv, fd
         return run, len(rowval), (4 if fd == 0 else 6), f"N={n} tridiagonal, 3 colours, {fdtype}"
     if workload == "c4":
         n = int(C4_N * scale) // C4_C * C4_C
@@ -680,6 +681,18 @@ def gpu_arm(args):
                                                "entries": int(got.size), "equal": equal,
                                                "mismatches": int((got != ref_nz).sum()) if not equal else 0}
             rec["parity"]["ok"] = bool(rec["parity"]["ok"] and equal)
+            try:
+                # the device's step sizes against the ones the reference's own `norm` gives (oracle: OpenBLAS dnrm2 restated
+                # in x87 extended precision, pinned bit for bit by tests/test_oracle_norm.py) — reported, in ulps
+                dev_eps = np.asarray(plan.eps(), dtype=np.float64)
+                ref_eps = np.array([orc.color_eps(run.x, run.cv, k + 1, run.fd) for k in range(dev_eps.size)])
+                ulps = (dev_eps - ref_eps) / np.spacing(np.abs(ref_eps))
+                rec["parity"]["eps_vs_reference_norm"] = {
+                    "against": "eps from LinearAlgebra.norm as the reference evaluates it (oracle fdo_norm2 = OpenBLAS dnrm2 for n >= 32)",
+                    "max_abs_ulps": float(np.max(np.abs(ulps))), "max_rel_err": float(np.max(np.abs(dev_eps / ref_eps - 1.0))),
+                    "bit_equal": int((dev_eps == ref_eps).sum()), "colors": int(dev_eps.size)}
+            except Exception as e:  # a diagnostic must never cost the headline line
+                rec["parity"]["eps_vs_reference_norm"] = {"error": repr(e)[:200]}
 
     # ---- the other BASELINE configs at full size on this GPU (sub-records of the one line)
     others = {}

@@ -22,10 +22,14 @@
  * tests hold for this path (test/coloring_tests.jl, test/cache_reuse_tests.jl,
  * test/finitedifftests.jl:398-463) — values to those tests' own tolerances,
  * f!-call counts/order and index sets exactly (tests/test_oracle_kat.py).
- * One piece of third-party arithmetic is NOT bit-pinned: Julia's
- * LinearAlgebra.norm (OpenBLAS dnrm2 for n>=32; Project.toml:30 julia>=1.10)
- * at jacobians.jl:560,601, restated here as sqrt(sum x^2) with sequential
- * summation.  It only determines eps; "bit-level eps: parity unpinned".
+ * Third-party arithmetic on the path: Julia's LinearAlgebra.norm at
+ * jacobians.jl:560,601 (stdlib generic_norm2 for n<32, OpenBLAS dnrm2 for n>=32;
+ * Project.toml:30 julia>=1.10; neither is under /root/reference).  fdo_norm2
+ * restates both; the dnrm2 half is pinned BIT FOR BIT against an OpenBLAS binary
+ * (tests/golden/dnrm2_openblas.json, tests/test_oracle_norm.py); the
+ * generic_norm2 half follows the published stdlib source and stays unexecuted
+ * ("parity unpinned" for n<32 at bit level; the reference's KATs with n=30 pin
+ * its values to their tolerances).  It only determines eps.
  */
 #ifndef FD_ORACLE_H
 #define FD_ORACLE_H
@@ -101,6 +105,8 @@ typedef struct {
   int64_t fcalls;        /* out: number of f! calls made */
 } fdo_opts;
 
+/* LinearAlgebra.norm(x::Vector{Float64}) as the reference evaluates it (see fd_oracle.c) */
+double fdo_norm2(const double *v, int64_t n);
 double fdo_default_relstep(int fdtype);
 double fdo_compute_epsilon(int fdtype, double x, double relstep, double absstep, double dir);
 int64_t fdo_max_color(const int64_t *colorvec, int64_t n);

@@ -88,6 +88,8 @@ def lib():
         if not _LIB_PATH.exists():
             build()
         L = C.CDLL(str(_LIB_PATH))
+        L.fdo_norm2.restype = C.c_double
+        L.fdo_norm2.argtypes = [C.c_void_p, C.c_int64]
         L.fdo_default_relstep.restype = C.c_double
         L.fdo_default_relstep.argtypes = [C.c_int]
         L.fdo_compute_epsilon.restype = C.c_double
@@ -124,6 +126,24 @@ def _pi64(a):
 
 def _as_i64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int64)
+
+
+def norm2(v) -> float:
+    """LinearAlgebra.norm of a Float64 vector as the reference evaluates it (generic_norm2 below 32 elements, OpenBLAS
+    dnrm2 from 32 on) — fd_oracle.c:fdo_norm2."""
+    a = np.ascontiguousarray(v, dtype=np.float64)
+    return lib().fdo_norm2(a.ctypes.data, a.size)
+
+
+def color_eps(x, colorvec, k: int, fdtype: int, relstep=None, absstep=None, dir: float = 1.0) -> float:
+    """Step size of colour k (1-based) exactly as jacobians.jl:559-561 / :600-602 form it from a pristine x:
+    x2 = x .* (colorvec .== k); eps = compute_epsilon(fd, sqrt(norm(x2)), relstep, absstep, dir)."""
+    x = np.asarray(x, dtype=np.float64)
+    mask = np.asarray(colorvec) == k
+    x2 = np.where(mask, x, np.copysign(0.0, x))
+    rs = default_relstep(fdtype) if relstep is None else relstep
+    ab = rs if absstep is None else absstep
+    return compute_epsilon(fdtype, float(np.sqrt(norm2(x2))), rs, ab, dir)
 
 
 def default_relstep(fdtype: int) -> float:

@@ -51,6 +51,39 @@ def compute_epsilon(fdtype, x, relstep, absstep, dir):
     return max(relstep * abs(x), absstep)                      # epsilons.jl:50-53
 
 
+def norm(x2):
+    """LinearAlgebra.norm(::Vector{Float64}) (stdlib: norm2 -> generic_norm2 below 32 elements, BLAS.nrm2 from 32 on),
+    written independently of oracle/fd_oracle.c: plain Python floats in order for the short branch, numpy's x87
+    `longdouble` with four interleaved accumulators for OpenBLAS's nrm2.S."""
+    n = len(x2)
+    if n == 0:
+        return 0.0
+    if n < 32:
+        maxabs = max(abs(float(v)) for v in x2)
+        if maxabs == 0.0 or math.isinf(maxabs):
+            return maxabs
+        if math.isfinite(n * maxabs * maxabs) and maxabs * maxabs != 0.0:
+            s = 0.0
+            for v in x2:
+                s += float(v) * float(v)
+            return math.sqrt(s)
+        s = 0.0
+        for v in x2:
+            t = abs(float(v)) / maxabs
+            s += t * t
+        return maxabs * math.sqrt(s)
+    L = np.longdouble
+    acc = [L(0), L(0), L(0), L(0)]
+    body = n - n % 8
+    for i in range(body):
+        t = L(x2[i])
+        acc[i % 4] = acc[i % 4] + t * t
+    for i in range(body, n):
+        t = L(x2[i])
+        acc[0] = acc[0] + t * t
+    return float(np.sqrt((acc[0] + acc[1]) + (acc[2] + acc[3])))
+
+
 def default_relstep(fdtype):
     eps = np.finfo(np.float64).eps
     return math.sqrt(eps) if fdtype == "forward" else float(np.cbrt(eps))   # epsilons.jl:134-144: sqrt(eps(T)) / cbrt(eps(T))
@@ -141,7 +174,7 @@ def finite_difference_jacobian(J, f, x, cache, f_in=None, *, fdtype="forward", r
             else:
                 mask = (_color == color_i)
                 x2[:] = x1 * mask                              # :559
-                tmp = float(np.sqrt(np.sum(x2 * x2)))          # norm(x2) :560  (bit-level: see DESIGN.md §2)
+                tmp = norm(x2)                                 # norm(x2) :560
                 epsilon = compute_epsilon("forward", math.sqrt(tmp), relstep, absstep, dir)   # :561
                 x1[:] = x1 + epsilon * mask                    # :562
                 f(fx1, x1); calls += 1                         # :563
@@ -164,7 +197,7 @@ def finite_difference_jacobian(J, f, x, cache, f_in=None, *, fdtype="forward", r
             else:
                 mask = (_color == color_i)
                 x2[:] = x1 * mask                              # :600
-                tmp = float(np.sqrt(np.sum(x2 * x2)))
+                tmp = norm(x2)                                 # :601
                 epsilon = compute_epsilon("central", math.sqrt(tmp), relstep, absstep, dir)
                 x1[:] = x1 + epsilon * mask                    # :603
                 x[:] = x - epsilon * mask                      # :604

@@ -2,7 +2,8 @@
 on random problems: every sparsity / J kind of the path, forward and central, random relstep / absstep / dir / f_in,
 colourings that are NOT valid (overlapping writes resolved by colour order) and colorvec entries < 1.  Fed the same step
 sizes the two restatements must agree bit for bit in J, in the f!-call count and in the drifted end state of cache.x1;
-their own step sizes must agree to reduction-order accuracy."""
+their own step sizes are bit-identical too: both evaluate `norm` as the reference does (stdlib generic_norm2 below 32
+components, OpenBLAS's x87 dnrm2 from 32 on — tests/test_oracle_norm.py pins that half against OpenBLAS itself)."""
 import numpy as np
 import pytest
 import scipy.sparse as sps
@@ -13,8 +14,10 @@ FD = {"forward": 0, "central": 1}
 KINDS = ["csc_same", "csc_to_dense", "proto_to_dense", "banded", "banded_to_dense", "dense_cols"]
 
 
-def _problem(rng, kind):
+def _problem(rng, kind, long_x=False):
     m, n = int(rng.integers(3, 24)), int(rng.integers(3, 24))
+    if long_x:                                   # 32 or more components: norm takes its BLAS (dnrm2) branch
+        n = int(rng.integers(32, 72))
     if kind in ("banded", "banded_to_dense"):
         l, u = int(rng.integers(0, 4)), int(rng.integers(0, 4))
         D = np.zeros((m, n), bool)
@@ -37,7 +40,7 @@ def _problem(rng, kind):
 @pytest.mark.parametrize("kind", KINDS)
 def test_oracle_matches_literal_transcription(oracle, kind, seed):
     rng = np.random.default_rng(1000 * seed + KINDS.index(kind))
-    m, n, l, u, D, f = _problem(rng, kind)
+    m, n, l, u, D, f = _problem(rng, kind, long_x=seed % 3 == 2)
     fdtype = "forward" if rng.random() < 0.5 else "central"
     x = rng.uniform(-2, 2, n)
     kw = {}
@@ -104,7 +107,9 @@ def test_oracle_matches_literal_transcription(oracle, kind, seed):
     Jo = np.full(Jl.size, np.nan)
     ro = oracle.jacobian(P, Jo, f, x.copy(), **okw)
     assert ro["fcalls"] == rl["fcalls"]
-    np.testing.assert_allclose(ro["eps"], rl["eps"], rtol=1e-14, atol=0)
+    # both restatements evaluate norm as the reference does (generic_norm2 / OpenBLAS dnrm2): same step sizes, same J
+    assert np.array_equal(ro["eps"], rl["eps"]), f"{kind} {fdtype} seed {seed}"
+    assert np.array_equal(Jo, Jl, equal_nan=True), f"{kind} {fdtype} seed {seed}"
     Jo2 = np.full(Jl.size, np.nan)
     cache_o = dict(x1=np.full(n, np.nan), x2=np.full(n, np.nan), fx=np.full(m, np.nan), fx1=np.full(m, np.nan))
     oracle.jacobian(P, Jo2, f, x.copy(), eps_override=None if kind == "dense_cols" else rl["eps"], cache=cache_o, **okw)
