@@ -691,6 +691,9 @@ def gpu_arm(args):
                     "against": "eps from LinearAlgebra.norm as the reference evaluates it (oracle fdo_norm2 = OpenBLAS dnrm2 for n >= 32)",
                     "max_abs_ulps": float(np.max(np.abs(ulps))), "max_rel_err": float(np.max(np.abs(dev_eps / ref_eps - 1.0))),
                     "bit_equal": int((dev_eps == ref_eps).sum()), "colors": int(dev_eps.size)}
+                if equal and bool((dev_eps == ref_eps).all()):
+                    # same step sizes => the oracle run above is also what the oracle computes entirely on its own
+                    rec["parity"]["oracle_bitwise"]["holds_with_the_oracles_own_step_sizes"] = True
             except Exception as e:  # a diagnostic must never cost the headline line
                 rec["parity"]["eps_vs_reference_norm"] = {"error": repr(e)[:200]}
 

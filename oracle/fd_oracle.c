@@ -165,6 +165,9 @@ static double generic_norm2(const double *v, int64_t n) {
   return maxabs * sqrt(sum);
 }
 
+#if LDBL_MANT_DIG != 64
+#warning "long double is not the x87 80-bit format here: fdo_norm2 will not reproduce OpenBLAS's x86-64 dnrm2 bit for bit (tests/test_oracle_norm.py will say so)"
+#endif
 static double openblas_dnrm2_x87(const double *v, int64_t n) {
   long double a0 = 0.0L, a1 = 0.0L, a2 = 0.0L, a3 = 0.0L;
   const int64_t body = n & ~(int64_t)7;
