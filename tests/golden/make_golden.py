@@ -105,6 +105,14 @@ def main():
         "fdtypes": ["forward", "central", "complex"],
         "rtol": float(np.sqrt(np.finfo(float).eps)),       # Julia's isapprox default for Float64
     }
+    # --- finitedifftests.jl:524-536: "Jacobian for non-vector inputs": x = rand(2,2), iipf(fx,x) = (fx .= x), J_ref = I(4),
+    #     in-place cache-less call with f_in = iipf(similar(x), x); err < 1e-8 for forward / central / complex ---
+    out["nonvector_identity"] = {
+        "cite": "test/finitedifftests.jl:524-536",
+        "x": rng.random((2, 2)).tolist(),
+        "bound": 1e-8,
+        "fdtypes": ["forward", "central", "complex"],
+    }
     # --- epsilons.jl:134-144 defaults ---
     out["default_relstep"] = {
         "cite": "src/epsilons.jl:134-144",

@@ -349,3 +349,26 @@ def test_identity_map_all_fdtypes(oracle, golden):
             r = oracle.jacobian(oracle.Problem.dense(2, 2), J, ident, x.copy(), fdtype=0 if fd == "forward" else 1)
             assert r["fcalls"] == (3 if fd == "forward" else 4)
         np.testing.assert_allclose(J.reshape(2, 2, order="F"), Jexp, rtol=g["rtol"], atol=g["rtol"])
+
+
+def test_nonvector_input_identity(oracle, golden):
+    # finitedifftests.jl:524-536: x = rand(2,2) (used as vec(x)), iipf(fx, x) = (fx .= x), J_ref = I(4); the in-place
+    # cache-less call gets f_in = iipf(similar(x), x); max abs error < 1e-8 for every fdtype
+    g = golden["nonvector_identity"]
+    x = np.array(g["x"]).reshape(-1, order="F")          # Julia's vec(): column-major
+
+    def ident(out, xx):
+        out[:] = xx
+
+    for fd in g["fdtypes"]:
+        J = np.full(16, np.nan)
+        if fd == "complex":
+            r = oracle.jacobian_complex(oracle.Problem.dense(4, 4), J, ident, x.copy())
+            assert r["fcalls"] == 4
+        elif fd == "forward":
+            r = oracle.jacobian(oracle.Problem.dense(4, 4), J, ident, x.copy(), fdtype=0, f_in=x.copy())
+            assert r["fcalls"] == 4                       # f_in given: no f(x) evaluation (jacobians.jl:540-545)
+        else:
+            r = oracle.jacobian(oracle.Problem.dense(4, 4), J, ident, x.copy(), fdtype=1)
+            assert r["fcalls"] == 8
+        assert np.max(np.abs(J.reshape(4, 4, order="F") - np.eye(4))) < g["bound"]
