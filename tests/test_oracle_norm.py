@@ -38,6 +38,11 @@ def test_golden_shows_what_a_plain_sum_would_miss():
 
 def test_norm_matches_openblas_dnrm2_live(oracle):
     blas = pytest.importorskip("scipy.linalg.blas")
+    # OpenBLAS picks its kernels per CPU at run time: only a host whose dnrm2 is the x87 kernel the fixture was recorded
+    # from can serve as a live reference (every x86-64 target known to us uses it; anything else is skipped, not failed)
+    probe = [c for c in _cases() if c["n"] <= 100003][:12]
+    if any(float(blas.dnrm2(vector(c["seed"], c["n"], c["kind"], c["scale_exp"]))).hex() != c["dnrm2_hex"] for c in probe):
+        pytest.skip("this host's OpenBLAS dnrm2 is not the kernel tests/golden/dnrm2_openblas.json was recorded from")
     rng = np.random.default_rng(77)
     for t in range(120):
         n = int(rng.integers(32, 300_000))
